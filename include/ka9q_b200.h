@@ -1,0 +1,271 @@
+/* ka9q_b200.h — C ABI of libka9q_b200.so: the B200 (sm_100a) receive-DSP hot path of ka9q-radio.
+ *
+ * Two layers, both plain C (pointers and sizes only; no CUDA or torch types):
+ *
+ *  A. DROP-IN layer — the reference's own symbols with the reference's own struct layouts, so `radio`,
+ *     `packet`, `modulate` and `hackrf` can link this library in place of filter.o / osc.o / decimate.o:
+ *        filter.h:81-92   create_filter_input/output, execute_filter_input/output, delete_*, set_filter,
+ *                         window_filter, window_rfilter, make_kaiser, noise_gain, Kaiser_beta
+ *        osc.h:21-24      set_osc, step_osc, renorm_osc, is_phasor_init
+ *        decimate.h:10-11 hb15_block, hb3_block
+ *     FFTs, bin selection/response multiply, filter design and the half-band FIRs run on the GPU; the host
+ *     buffers the callers poke directly (in->input.c, in->fdomain, out->output.c, out->response ...) are kept
+ *     coherent mirrors. The oscillator is host-side scalar state by nature (one complex-double multiply per call).
+ *
+ *  B. BATCH layer (ka9q_*) — the channelizer the drop-in layer cannot express: ONE forward FFT per I/Q stream
+ *     block shared by thousands of channels, each channel = bin rotation + response multiply + 2048-point
+ *     inverse FFT + overlap discard + fused demodulator (FM / AM / linear) + int16 PCM. It replaces, per channel,
+ *     one whole `radio` process: proc_samples (radio.c:41-150) -> execute_filter_input (filter.c:146) ->
+ *     execute_filter_output (filter.c:175) -> demod_fm / demod_am / demod_linear (fm.c:21, am.c:15, linear.c:21)
+ *     -> scaleclip (audio.c:22-28). Mode rows (modes.txt -> struct modetab, radio.h:33-48) and RTP I/O stay in C
+ *     on the host and feed ka9q_chan_params / consume the PCM rows.
+ *
+ * All functions return 0 on success and a negative value on error unless stated otherwise;
+ * ka9q_last_error() returns a thread-local description. There is NO CPU fallback: without a usable CUDA device
+ * every compute entry point fails.
+ */
+#ifndef KA9Q_B200_H
+#define KA9Q_B200_H 1
+
+#include <pthread.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#define KA9Q_CFLOAT void /* complex float * in C */
+#else
+#include <complex.h>
+#define KA9Q_CFLOAT complex float
+#endif
+
+/* ====================================================================================================
+ * A. Drop-in layer
+ * ==================================================================================================== */
+
+/* reference filter.h:17-22 */
+enum filtertype {
+  NONE,
+  COMPLEX,
+  CROSS_CONJ, /* COMPLEX output with the cross-conjugation used for ISB (filter.c:239-249) */
+  REAL,
+};
+
+/* reference filter.h:25-28 */
+union rc {
+  float *r;
+  KA9Q_CFLOAT *c;
+};
+
+/* Binary-compatible with reference filter.h:54-66 (callers read/write fields directly: radio.c:89,139-140;
+ * fm.c:131,141,160; radio.c:388-396 reads fdomain/ilen/impulse_length). fwd_plan is an opaque handle here. */
+struct filter_in {
+  enum filtertype in_type;       /* REAL or COMPLEX */
+  unsigned int ilen;             /* L: user samples per block */
+  unsigned int impulse_length;   /* M: impulse response length */
+  KA9Q_CFLOAT *fdomain;          /* spectrum mirror: N bins (COMPLEX) or N/2+1 (REAL) */
+  union rc input_buffer;         /* N = L + M - 1 samples */
+  union rc input;                /* input_buffer + (M-1): the caller writes L new samples here */
+  void *fwd_plan;                /* opaque (device context) */
+  unsigned int blocknum;         /* incremented by execute_filter_input */
+  pthread_mutex_t filter_mutex;
+  pthread_cond_t filter_cond;
+};
+
+/* Binary-compatible with reference filter.h:67-80 (fm.c:93-94,129,169-170; am.c:55-56; linear.c:117-120,140-148,
+ * 211-213,254,280,286,295,299; radio_status.c:171). */
+struct filter_out {
+  struct filter_in *master;
+  enum filtertype out_type;
+  KA9Q_CFLOAT *response;         /* owned by the slave once passed in (filter.c:271, :539-543) */
+  pthread_mutex_t response_mutex;
+  KA9Q_CFLOAT *f_fdomain;
+  float noise_gain;
+  union rc output_buffer;        /* N/decimate samples */
+  union rc output;               /* output_buffer + N/decimate - olen */
+  void *rev_plan;                /* opaque (device context) */
+  unsigned int decimate;
+  unsigned int olen;
+  unsigned int blocknum;
+};
+
+/* filter.h:81-92 */
+int window_filter(int L, int M, KA9Q_CFLOAT *response, float beta);
+int window_rfilter(int L, int M, KA9Q_CFLOAT *response, float beta);
+struct filter_in *create_filter_input(unsigned int L, unsigned int M, enum filtertype in_type);
+struct filter_out *create_filter_output(struct filter_in *master, KA9Q_CFLOAT *response, unsigned int decimate,
+                                        enum filtertype out_type);
+int execute_filter_input(struct filter_in *);
+int execute_filter_output(struct filter_out *);
+int delete_filter_input(struct filter_in *);
+int delete_filter_output(struct filter_out *);
+int make_kaiser(float *window, unsigned int M, float beta);
+int set_filter(struct filter_out *, float low, float high, float kaiser_beta);
+float noise_gain(struct filter_out const *);
+extern float Kaiser_beta; /* filter.c:279 */
+
+/* Allocation helpers for `response` buffers handed to create_filter_output (the reference uses
+ * fftwf_alloc_complex / fftwf_free; a drop-in build maps those two names onto these). */
+void *ka9q_alloc(size_t bytes);
+void ka9q_free(void *p);
+
+/* reference osc.h:9-24 */
+#ifndef __cplusplus
+struct osc {
+  double freq;
+  double rate;
+  complex double phasor;
+  complex double phasor_step;
+  complex double phasor_step_step;
+  pthread_mutex_t mutex;
+  int steps;
+};
+void set_osc(struct osc *osc, double f, double r);
+complex double step_osc(struct osc *osc);
+void renorm_osc(struct osc *osc);
+int is_phasor_init(const complex double x);
+#endif
+
+/* reference decimate.h:4-11 */
+struct hb15_state {
+  float coeffs[4];
+  float even_samples[4];
+  float odd_samples[4];
+  float old_odd_samples[4];
+};
+void hb15_block(struct hb15_state *state, float *output, float *input, int cnt);
+void hb3_block(float *state, float *output, float *input, int cnt);
+
+/* ====================================================================================================
+ * B. Batch layer
+ * ==================================================================================================== */
+
+typedef struct ka9q_stream ka9q_stream;
+
+/* enum demod_type (radio.h:20-24) */
+#define KA9Q_LINEAR_DEMOD 0
+#define KA9Q_AM_DEMOD 1
+#define KA9Q_FM_DEMOD 2
+/* option flags of a mode row (modes.c:104-120) */
+#define KA9Q_FLAG_ISB 1
+#define KA9Q_FLAG_FLAT 2
+#define KA9Q_FLAG_PLL 4
+#define KA9Q_FLAG_SQUARE 8
+/* wire formats of the I/Q input (multicast.h:19-24; radio.c:60-68,111-119) */
+#define KA9Q_IQ_S16 1
+#define KA9Q_IQ_S8 2
+
+/* One receive channel = the per-channel part of struct demod (radio.h:64-193) after set_mode (radio.c:322-374). */
+typedef struct ka9q_chan_params {
+  int demod_type;        /* KA9Q_*_DEMOD */
+  int flags;             /* KA9Q_FLAG_* */
+  int channels;          /* 1 = mono, 2 = stereo I/Q (linear only) */
+  int reserved;
+  long long bin;         /* carrier on the N-point grid: f_c = bin * samprate / N (second LO = -f_c, radio.c:217) */
+  float low, high;       /* filter edges, Hz (demod->filter.low/high) */
+  float kaiser_beta;     /* demod->filter.kaiser_beta (main.c:115: 3.0) */
+  float shift;           /* post-detection shift, Hz (demod->tune.shift; linear only) */
+  float attack_rate;     /* dB/s, unused by the reference demodulators (am.c:28, linear.c:34-36) */
+  float recovery_rate;   /* dB/s */
+  float hangtime;        /* s */
+  float headroom;        /* amplitude ratio; NAN -> pow(10,-15/20) (main.c:117) */
+} ka9q_chan_params;
+
+/* Per-channel, per-block status: the demod->sig.* scalars the reference publishes (radio.h:155-166). */
+typedef struct ka9q_chan_status {
+  float bb_power;
+  float snr;
+  float foffset;
+  float pdeviation;
+  float agc_gain;
+  int squelch_open;
+  float reserved[2];
+} ka9q_chan_status;
+
+typedef struct ka9q_stream_config {
+  int device;            /* CUDA device ordinal */
+  int samprate;          /* input sample rate, Hz */
+  int L, M;              /* block and impulse lengths at the input rate (main.c:113-114) */
+  int decimate;          /* samprate / output rate (radio_status.c:266); N/decimate must be 2048 */
+  int iq_format;         /* KA9Q_IQ_S16 or KA9Q_IQ_S8 */
+  float gain_factor;     /* demod->sdr.gain_factor (radio.c:122) */
+  int max_blocks;        /* blocks processed per ka9q_stream_process call (>=1) */
+  int capture_filter_output; /* nonzero: keep raw filter output for ka9q_stream_get_filter_output (tests) */
+} ka9q_stream_config;
+
+/* pinned (page-locked) host memory for I/Q and PCM buffers */
+void *ka9q_host_alloc(size_t bytes);
+void ka9q_host_free(void *p);
+
+const char *ka9q_last_error(void);
+const char *ka9q_version(void);
+/* number of usable CUDA devices (0 if none); never fails */
+int ka9q_device_count(void);
+
+int ka9q_stream_create(ka9q_stream **out, const ka9q_stream_config *cfg);
+int ka9q_stream_destroy(ka9q_stream *s);
+/* Add a channel; returns its index (>=0) or a negative error. Channels can only be added before commit. */
+int ka9q_stream_add_channel(ka9q_stream *s, const ka9q_chan_params *p);
+/* Designs all channel filters on the device (set_filter, filter.c:500-546), uploads parameters, allocates buffers. */
+int ka9q_stream_commit(ka9q_stream *s);
+/* Re-design one channel's filter after commit (the UI path: display.c:163-177). */
+int ka9q_stream_set_filter(ka9q_stream *s, int chan, float low, float high, float kaiser_beta);
+
+int ka9q_stream_num_channels(const ka9q_stream *s);
+/* int16 units per block row of the PCM output, and a channel's offset / channel count inside the row */
+long long ka9q_stream_pcm_stride(const ka9q_stream *s);
+int ka9q_stream_pcm_offset(const ka9q_stream *s, int chan);
+int ka9q_stream_olen(const ka9q_stream *s);
+int ka9q_stream_fft_size(const ka9q_stream *s);
+int ka9q_stream_launches_per_call(const ka9q_stream *s);
+
+/* End-to-end call. iq: nblocks*L interleaved I/Q samples in HOST memory (int16 or int8 per iq_format).
+ * pcm: HOST buffer of nblocks * pcm_stride int16; status: HOST buffer of nblocks * nchan entries or NULL.
+ * Copies H2D, runs forward FFT + all channels, copies D2H, returns when the results are in pcm/status. */
+int ka9q_stream_process(ka9q_stream *s, const void *iq, int nblocks, int16_t *pcm, ka9q_chan_status *status);
+
+/* Split form for pipelining and device-resident benchmarking:
+ *   push     : H2D copy of nblocks*L samples into the device ring (async on the stream's copy stream)
+ *   compute  : forward FFT + channel kernels for the nblocks most recently pushed (async)
+ *   fetch    : D2H copy of PCM/status of the last compute (async)
+ *   sync     : wait for everything issued so far
+ * ka9q_stream_compute_resident re-runs compute on the samples already in the ring (inputs resident in HBM). */
+int ka9q_stream_push(ka9q_stream *s, const void *iq, int nblocks);
+int ka9q_stream_compute(ka9q_stream *s, int nblocks);
+int ka9q_stream_compute_resident(ka9q_stream *s, int nblocks);
+int ka9q_stream_fetch(ka9q_stream *s, int nblocks, int16_t *pcm, ka9q_chan_status *status);
+int ka9q_stream_sync(ka9q_stream *s);
+/* Time of the device work of the last compute call in milliseconds (CUDA events on the compute stream), and of
+ * the dominant (channel) kernels alone. Valid after ka9q_stream_sync. */
+int ka9q_stream_last_timing(ka9q_stream *s, float *total_ms, float *fft_ms, float *chan_ms);
+
+/* Multi-GPU: channels are sharded by the caller (each rank adds only its own channels); the rank that owns the
+ * I/Q input runs the forward FFT and broadcasts the spectrum. The caller supplies the broadcast as a callback
+ * (NCCL in bench.py through torch.distributed, or ka9q_nccl_* below). When root < 0 every rank computes its own FFT. */
+int ka9q_stream_spectrum_ptr(ka9q_stream *s, void **dev_ptr, long long *bytes_per_block);
+int ka9q_stream_compute_fft_only(ka9q_stream *s, int nblocks);
+int ka9q_stream_compute_channels_only(ka9q_stream *s, int nblocks);
+/* NCCL spectrum broadcast inside the library (libnccl.so.2 is dlopen'ed on first use). */
+int ka9q_nccl_unique_id(void *id128);
+int ka9q_stream_nccl_init(ka9q_stream *s, const void *id128, int rank, int nranks);
+int ka9q_stream_nccl_broadcast_spectrum(ka9q_stream *s, int nblocks, int root);
+
+/* Introspection for parity tests (device -> host copies, synchronous). */
+int ka9q_stream_get_response(ka9q_stream *s, int chan, KA9Q_CFLOAT *out2048, float *noise_gain);
+int ka9q_stream_get_filter_output(ka9q_stream *s, int chan, int nblocks, KA9Q_CFLOAT *out /* nblocks*olen */);
+int ka9q_stream_get_spectrum(ka9q_stream *s, int block, KA9Q_CFLOAT *outN);
+int ka9q_stream_get_if_energy(ka9q_stream *s, int nblocks, float *energy /* sum |x|^2 per block */);
+
+/* Generic batched complex FFT on host buffers (cross-checks and tests): sign -1 forward, +1 backward. */
+int ka9q_fft_c2c(int device, int n, int batch, int sign, const KA9Q_CFLOAT *in, KA9Q_CFLOAT *out);
+/* How n would be factorised into passes: fills sizes[0..3], returns number of passes or -1 if unsupported. */
+int ka9q_fft_plan_describe(int n, int *sizes);
+
+/* Half-band decimator cascade on the device (decimate.c:44-162 driven as hackrf.c:297-318):
+ * `stages` x (15-tap half-band /2), highest rate first, separately per plane; state16 holds stages x hb15_state. */
+int ka9q_hb15_cascade(int device, int stages, struct hb15_state *states, const float *in, int n_in, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KA9Q_B200_H */

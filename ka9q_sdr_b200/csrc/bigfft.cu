@@ -1,0 +1,357 @@
+// K1+K2 implementation: see bigfft.cuh.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "bigfft.cuh"
+#include "fft_regs.cuh"
+#include "util.cuh"
+
+namespace k9 {
+
+// ---------------- device side ----------------
+
+__device__ __forceinline__ float2 load_input(const PassArgs& a, int batch, int idx) {
+  switch (a.in_mode) {
+    default:
+    case IN_C32:
+      return reinterpret_cast<const float2*>(a.in)[(long long)batch * a.in_batch_stride + idx];
+    case IN_RING_S16: {
+      long long pos = a.ring_off + (long long)batch * a.ring_step + idx;
+      pos %= a.ring_cap;
+      short2 v = reinterpret_cast<const short2*>(a.in)[pos];
+      // reference radio.c:113-114,122: (float)int16 * SCALE16, then * gain_factor
+      return make_float2(((float)v.x * a.scale) * a.gain, ((float)v.y * a.scale) * a.gain);
+    }
+    case IN_RING_S8: {
+      long long pos = a.ring_off + (long long)batch * a.ring_step + idx;
+      pos %= a.ring_cap;
+      char2 v = reinterpret_cast<const char2*>(a.in)[pos];
+      return make_float2(((float)v.x * a.scale) * a.gain, ((float)v.y * a.scale) * a.gain);
+    }
+    case IN_RING_C32: {
+      long long pos = a.ring_off + (long long)batch * a.ring_step + idx;
+      pos %= a.ring_cap;
+      return reinterpret_cast<const float2*>(a.in)[pos];
+    }
+    case IN_RING_R32: {
+      long long pos = a.ring_off + (long long)batch * a.ring_step + idx;
+      pos %= a.ring_cap;
+      return make_float2(reinterpret_cast<const float*>(a.in)[pos], 0.f);
+    }
+  }
+}
+
+template <int SIGN>
+__device__ __forceinline__ float2 big_twiddle(const PassArgs& a, unsigned e) {
+  // W_N^e = lo[e & 1023] * hi[e >> 10]
+  float2 lo = __ldg(a.tw_lo + (e & 1023u));
+  float2 hi = __ldg(a.tw_hi + (e >> 10));
+  float2 w = cmul(lo, hi);
+  if (SIGN > 0) w.y = -w.y;
+  return w;
+}
+
+// One Stockham pass: T columns per CTA, R = R1*R2 points per column.
+// Sub-pass A: radix R1, thread (col, p) p in [0,R2): loads x[c + ncols*(p + R2*r)], r<R1; writes u[R1*p + j] * W_R^(p*j)
+// Sub-pass B: radix R2, thread (col, q) q in [0,R1): loads u[q + R1*r], r<R2; output index jt = q + R1*j.
+template <int R1, int R2, int T, int SIGN, bool QFAST>
+__global__ void __launch_bounds__(T*(R1 > R2 ? R1 : R2)) fft_pass_kernel(const PassArgs a) {
+  constexpr int R = R1 * R2;
+  constexpr int S = R + 1;  // padded column stride (float2 units)
+  extern __shared__ float2 sm[];
+  const int tid = threadIdx.x;
+  const int batch = blockIdx.y;
+  const int col0 = blockIdx.x * T;
+  const int s = a.N / a.n_cur;
+
+  // ---- sub-pass A ----
+  float esum = 0.f;
+  if (tid < T * R2) {
+    const int col = tid % T;
+    const int p = tid / T;
+    const int c = col0 + col;
+    float2 v[R1];
+    if (c < a.ncols) {
+#pragma unroll
+      for (int r = 0; r < R1; r++) {
+        const int idx = c + a.ncols * (p + R2 * r);
+        v[r] = load_input(a, batch, idx);
+        if (a.energy != nullptr && idx >= a.stat_from) esum += v[r].x * v[r].x + v[r].y * v[r].y;
+      }
+      Dft<R1, SIGN>::run(v);
+#pragma unroll
+      for (int j = 0; j < R1; j++) {
+        float2 o = v[j];
+        if (j > 0 && p > 0) {
+          float2 w = __ldg(a.tw_r + p * j);
+          if (SIGN > 0) w.y = -w.y;
+          o = cmul(o, w);
+        }
+        sm[col * S + R1 * p + j] = o;
+      }
+    }
+  }
+  if (a.energy != nullptr) {
+    // warp-shuffle reduction at a convergent point, one atomic per warp
+    // (status only: numerator of demod->sig.if_power, reference radio.c:123,143-144)
+    esum = warp_sum(esum);
+    if ((tid & 31) == 0 && esum != 0.f) atomicAdd(a.energy + batch, esum);
+  }
+  __syncthreads();
+  // ---- sub-pass B ----
+  if (tid < T * R1) {
+    const int col = QFAST ? tid / R1 : tid % T;
+    const int q = QFAST ? tid % R1 : tid / T;
+    const int c = col0 + col;
+    if (c < a.ncols) {
+      float2 v[R2];
+#pragma unroll
+      for (int r = 0; r < R2; r++) v[r] = sm[col * S + q + R1 * r];
+      Dft<R2, SIGN>::run(v);
+      const int qg = c % s;
+      const int pg = c / s;
+      float2* out = a.out + (long long)batch * a.out_batch_stride + qg + (long long)s * ((long long)R * pg);
+      const bool last = (a.n_cur == R);
+#pragma unroll
+      for (int j = 0; j < R2; j++) {
+        const int jt = q + R1 * j;
+        float2 o = v[j];
+        if (!last) {
+          const unsigned e = (unsigned)pg * (unsigned)jt * (unsigned)s;  // < N
+          if (e != 0) o = cmul(o, big_twiddle<SIGN>(a, e));
+        }
+        out[(long long)s * jt] = o;
+      }
+    }
+  }
+}
+
+// ---------------- host side ----------------
+
+struct PassKind {
+  int R1, R2, T;
+};
+static const PassKind kKinds[] = {
+    {16, 16, 16}, {20, 16, 16}, {10, 16, 16}, {8, 16, 16}, {5, 16, 16}, {8, 8, 32}, {4, 8, 32},
+    {4, 4, 64},   {20, 20, 8},  {10, 10, 16}, {5, 10, 16}, {5, 5, 32},  {3, 16, 16}, {6, 16, 16}, {12, 16, 16}, {15, 16, 16},
+};
+static const int kNumKinds = sizeof(kKinds) / sizeof(kKinds[0]);
+
+template <int R1, int R2, int T>
+static cudaError_t launch_kind(const PassArgs& a, int batch, int sign, bool qfast, cudaStream_t st) {
+  constexpr int R = R1 * R2;
+  constexpr int threads = T * (R1 > R2 ? R1 : R2);
+  const size_t smem = sizeof(float2) * (size_t)T * (R + 1);
+  dim3 grid((a.ncols + T - 1) / T, batch);
+  static_assert(sizeof(float2) * (size_t)T * (R + 1) <= 48 * 1024, "pass tile must fit the default smem window");
+  auto set = [](auto) {};
+  if (sign < 0) {
+    if (qfast) {
+      set(fft_pass_kernel<R1, R2, T, -1, true>);
+      fft_pass_kernel<R1, R2, T, -1, true><<<grid, threads, smem, st>>>(a);
+    } else {
+      set(fft_pass_kernel<R1, R2, T, -1, false>);
+      fft_pass_kernel<R1, R2, T, -1, false><<<grid, threads, smem, st>>>(a);
+    }
+  } else {
+    if (qfast) {
+      set(fft_pass_kernel<R1, R2, T, +1, true>);
+      fft_pass_kernel<R1, R2, T, +1, true><<<grid, threads, smem, st>>>(a);
+    } else {
+      set(fft_pass_kernel<R1, R2, T, +1, false>);
+      fft_pass_kernel<R1, R2, T, +1, false><<<grid, threads, smem, st>>>(a);
+    }
+  }
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_pass(int R1, int R2, const PassArgs& a, int batch, int sign, bool qfast, cudaStream_t st) {
+#define K9_CASE(r1, r2, t) \
+  if (R1 == r1 && R2 == r2) return launch_kind<r1, r2, t>(a, batch, sign, qfast, st);
+  K9_CASE(16, 16, 16)
+  K9_CASE(20, 16, 16)
+  K9_CASE(10, 16, 16)
+  K9_CASE(8, 16, 16)
+  K9_CASE(5, 16, 16)
+  K9_CASE(8, 8, 32)
+  K9_CASE(4, 8, 32)
+  K9_CASE(4, 4, 64)
+  K9_CASE(20, 20, 8)
+  K9_CASE(10, 10, 16)
+  K9_CASE(5, 10, 16)
+  K9_CASE(5, 5, 32)
+  K9_CASE(3, 16, 16)
+  K9_CASE(6, 16, 16)
+  K9_CASE(12, 16, 16)
+  K9_CASE(15, 16, 16)
+#undef K9_CASE
+  return cudaErrorInvalidValue;
+}
+
+// Enumerate factorisations into supported pass sizes; prefer the fewest passes, then the smallest largest pass
+// (small tiles = more CTAs in flight), then the largest smallest pass.
+struct FactorBest {
+  int depth = 99;
+  int maxR = 1 << 30;
+  int minR = 0;
+  int pick[4];
+};
+static void factor_dfs(long long n, int depth, int start, int* pick, FactorBest& best) {
+  if (n == 1) {
+    if (depth == 0) return;
+    int mx = 0, mn = 1 << 30;
+    for (int i = 0; i < depth; i++) {
+      int R = kKinds[pick[i]].R1 * kKinds[pick[i]].R2;
+      mx = R > mx ? R : mx;
+      mn = R < mn ? R : mn;
+    }
+    bool better = depth < best.depth || (depth == best.depth && (mx < best.maxR || (mx == best.maxR && mn > best.minR)));
+    if (better) {
+      best.depth = depth;
+      best.maxR = mx;
+      best.minR = mn;
+      for (int i = 0; i < depth; i++) best.pick[i] = pick[i];
+    }
+    return;
+  }
+  if (depth == 4 || depth >= best.depth) return;
+  for (int i = start; i < kNumKinds; i++) {
+    const int R = kKinds[i].R1 * kKinds[i].R2;
+    if (n % R == 0) {
+      pick[depth] = i;
+      factor_dfs(n / R, depth + 1, i, pick, best);
+    }
+  }
+}
+
+int bigfft_factorize(int N, int* R1, int* R2) {
+  if (N < 16) return -1;
+  FactorBest best;
+  int pick[4];
+  // allow equal-depth alternatives to be compared: search with depth bound relaxed by re-running per depth
+  for (int maxd = 1; maxd <= 4; maxd++) {
+    best = FactorBest();
+    best.depth = maxd + 1;
+    factor_dfs(N, 0, 0, pick, best);
+    if (best.depth <= maxd) break;
+  }
+  if (best.depth > 4) return -1;
+  const int d = best.depth;
+  // ascending size: the strided first pass is the small one, the contiguous last pass the large one
+  for (int i = 0; i < d; i++)
+    for (int j = i + 1; j < d; j++) {
+      int ri = kKinds[best.pick[i]].R1 * kKinds[best.pick[i]].R2, rj = kKinds[best.pick[j]].R1 * kKinds[best.pick[j]].R2;
+      if (rj < ri) {
+        int t = best.pick[i];
+        best.pick[i] = best.pick[j];
+        best.pick[j] = t;
+      }
+    }
+  for (int i = 0; i < d; i++) {
+    R1[i] = kKinds[best.pick[i]].R1;
+    R2[i] = kKinds[best.pick[i]].R2;
+  }
+  return d;
+}
+
+int bigfft_plan_create(BigFftPlan* plan, int N) {
+  memset(plan, 0, sizeof(*plan));
+  int np = bigfft_factorize(N, plan->R1, plan->R2);
+  if (np < 0) return -1;
+  plan->N = N;
+  plan->npass = np;
+  cudaGetDevice(&plan->device);
+  // W_N tables in double, rounded once to float
+  const int nlo = 1024;
+  const int nhi = (N + 1023) / 1024;
+  std::vector<float2> lo(nlo), hi(nhi);
+  for (int a = 0; a < nlo; a++) {
+    double ang = -2.0 * M_PI * (double)(a % N) / (double)N;
+    lo[a] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+  for (int b = 0; b < nhi; b++) {
+    double ang = -2.0 * M_PI * (double)(((long long)b * 1024) % N) / (double)N;
+    hi[b] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+  if (cudaMalloc(&plan->tw_lo, sizeof(float2) * nlo) != cudaSuccess) return -2;
+  if (cudaMalloc(&plan->tw_hi, sizeof(float2) * nhi) != cudaSuccess) return -2;
+  cudaMemcpy(plan->tw_lo, lo.data(), sizeof(float2) * nlo, cudaMemcpyHostToDevice);
+  cudaMemcpy(plan->tw_hi, hi.data(), sizeof(float2) * nhi, cudaMemcpyHostToDevice);
+  for (int p = 0; p < np; p++) {
+    const int R = plan->R1[p] * plan->R2[p];
+    std::vector<float2> tr(R);
+    for (int a = 0; a < R; a++) {
+      double ang = -2.0 * M_PI * (double)a / (double)R;
+      tr[a] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    if (cudaMalloc(&plan->tw_r[p], sizeof(float2) * R) != cudaSuccess) return -2;
+    cudaMemcpy(plan->tw_r[p], tr.data(), sizeof(float2) * R, cudaMemcpyHostToDevice);
+  }
+  return 0;
+}
+
+void bigfft_plan_destroy(BigFftPlan* plan) {
+  if (!plan) return;
+  cudaFree(plan->tw_lo);
+  cudaFree(plan->tw_hi);
+  for (int p = 0; p < 4; p++) cudaFree(plan->tw_r[p]);
+  memset(plan, 0, sizeof(*plan));
+}
+
+int bigfft_exec(const BigFftPlan* plan, const BigFftIn& in, float2* out, long long out_batch_stride, float2* tmp0,
+                float2* tmp1, int batch, int sign, cudaStream_t stream) {
+  const int N = plan->N;
+  int n_cur = N;
+  const void* cur_in = in.in;
+  long long cur_stride = in.in_batch_stride;
+  int cur_mode = in.in_mode;
+  for (int p = 0; p < plan->npass; p++) {
+    const int R = plan->R1[p] * plan->R2[p];
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = cur_in;
+    a.in_batch_stride = cur_stride;
+    a.in_mode = cur_mode;
+    const bool lastpass = (p == plan->npass - 1);
+    float2* dst;
+    long long dst_stride;
+    if (lastpass) {
+      dst = out;
+      dst_stride = out_batch_stride;
+    } else {
+      // ping-pong: never write the buffer being read
+      dst = (cur_in == (const void*)tmp0) ? tmp1 : tmp0;
+      dst_stride = N;
+      if (!dst) return -3;
+    }
+    a.out = dst;
+    a.out_batch_stride = dst_stride;
+    a.N = N;
+    a.n_cur = n_cur;
+    a.ncols = N / R;
+    a.ring_cap = in.ring_cap;
+    a.ring_off = in.ring_off;
+    a.ring_step = in.ring_step;
+    a.scale = in.scale;
+    a.gain = in.gain;
+    a.stat_from = in.stat_from;
+    a.energy = (p == 0) ? in.energy : nullptr;
+    a.tw_lo = plan->tw_lo;
+    a.tw_hi = plan->tw_hi;
+    a.tw_r = plan->tw_r[p];
+    cudaError_t e = launch_pass(plan->R1[p], plan->R2[p], a, batch, sign, /*qfast=*/(N / n_cur) == 1, stream);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "bigfft: launch failed: %s\n", cudaGetErrorString(e));
+      return -4;
+    }
+    n_cur /= R;
+    cur_in = dst;
+    cur_stride = dst_stride;
+    cur_mode = IN_C32;
+  }
+  return 0;
+}
+
+}  // namespace k9

@@ -1,0 +1,86 @@
+// K3: per-channel fused kernels — shared declarations (device structs + host launchers).
+//
+// One work item = what one reference `radio` process does per 20 ms block after its forward FFT:
+// execute_filter_output (reference filter.c:175-252) -> demod_fm / demod_am / demod_linear per-sample loops
+// (fm.c:72-173, am.c:43-79, linear.c:114-311) -> scaleclip (audio.c:22-28).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace k9 {
+
+constexpr int NDEC = 2048;    // decimated FFT size the fused kernels are specialised for
+constexpr int OLEN_MAX = 1024;
+
+enum DemodType : int { DEMOD_LINEAR = 0, DEMOD_AM = 1, DEMOD_FM = 2 };  // reference radio.h:20-24
+enum ChanFlags : int { CH_ISB = 1, CH_FLAT = 2, CH_PLL = 4, CH_SQUARE = 8 };
+
+struct ChanParams {
+  long long bin;         // carrier position on the N-point grid, normalised to [0,N); second LO = -bin*Fs/N
+  int demod;
+  int flags;
+  int channels;          // PCM channels (1 mono, 2 stereo I/Q)
+  int pcm_off;           // int16 offset of this channel inside one block row of the PCM output
+  float fm_gain;         // (headroom * M_1_PI * dsamprate) / fabsf(low - high)   (fm.c:86)
+  float headroom;        // demod->agc.headroom (main.c:117)
+  float recovery_factor; // dB2voltage(recovery_rate * samptime)  (am.c:27, linear.c:33)
+  int hangmax;           // hangtime / samptime (am.c:29, linear.c:37)
+  double shift_cycles;   // post-detection shift, cycles per output sample (radio.c:313)
+  int audio_slot;        // FM: index of the audio (de-emphasis) response, -1 = flat
+  int pad_;
+};
+
+struct ChanState {
+  float2 fm_state;       // conj(last good sample) (fm.c:26,132)
+  float fm_lastaudio;    // fm.c:68
+  int fm_below;          // snr_below_threshold (fm.c:69)
+  float fm_foffset, fm_pdeviation;  // persist while squelch closed (fm.c:145-154)
+  float agc_gain;        // demod->agc.gain
+  float am_dc;           // DC_filter (am.c:33)
+  int hang;              // hangcount
+  int pad_;
+  double shift_phase;    // turns, phase of the post-detection shift oscillator at the start of the next block
+};
+
+struct ChanStatus {      // mirrors the demod->sig.* scalars the reference demodulators publish
+  float bb_power;        // fm.c:99, am.c:78, linear.c:302
+  float snr;             // fm.c:102-103 (NAN for AM / non-PLL linear, linear.c:309)
+  float foffset;         // fm.c:147
+  float pdeviation;      // fm.c:152
+  float agc_gain;        // demod->agc.gain after the block
+  int squelch_open;      // FM: snr_below_threshold < 2
+  float reserved[2];
+};
+
+struct ChanLaunch {
+  // shared per-stream data
+  const float2* spec;        // [nblocks][N] forward spectra
+  long long spec_stride;     // N
+  int N;                     // forward FFT size
+  int L, M;                  // block length / impulse length at the input rate (for the per-block LO phase)
+  int olen;                  // output samples per block (960)
+  float dsamprate;           // decimated (output) sample rate, (float)samprate / decimate (fm.c:27)
+  int nblocks;
+  long long block0;          // index of the first block of this launch since stream start
+  const float2* tw2048;      // W_2048 table
+  // per-channel arrays
+  const ChanParams* params;
+  ChanState* state;
+  const float2* resp;        // [nchan][2048] channel responses H (filter_out.response)
+  const float2* audio_resp;  // [naudio][2048] full-length (Hermitian-extended) FM audio responses
+  float* audio_hist;         // [nchan][2048] FM audio ring (history M_audio-1 = 1088 samples + 960 new)
+  int16_t* pcm;              // [nblocks][pcm_stride]
+  long long pcm_stride;
+  ChanStatus* status;        // [nblocks][nchan_total]
+  int nchan_total;
+  float2* filt_dbg;          // optional [nblocks][nchan_total][olen] raw filter output capture (parity tests), or null
+  // work list for this launch
+  const int2* work;          // FM: (chanA, chanB or -1); AM / linear: (chan, -1)
+  int nwork;
+};
+
+int launch_fm(const ChanLaunch& a, cudaStream_t st);
+int launch_am(const ChanLaunch& a, cudaStream_t st);
+int launch_linear(const ChanLaunch& a, cudaStream_t st);
+
+}  // namespace k9

@@ -1,0 +1,818 @@
+// Batch layer host side (C++ behind the C ABI of include/ka9q_b200.h, section B): one I/Q stream on one GPU,
+// K channels. Owns the device I/Q ring, the spectrum buffers, per-channel parameter/state/response arrays and the
+// CUDA streams; designs filters (K4), runs the forward FFT (K1+K2) once per block and the fused channel kernels (K3).
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <vector>
+#include "../../include/ka9q_b200.h"
+#include "bigfft.cuh"
+#include "chan.cuh"
+#include "design.cuh"
+#include "util.cuh"
+
+namespace k9 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+}  // namespace k9
+
+using namespace k9;
+
+#define K9_CHECK(cond, ...)        \
+  do {                             \
+    if (!(cond)) {                 \
+      k9::set_error(__VA_ARGS__);  \
+      return -1;                   \
+    }                              \
+  } while (0)
+
+struct ka9q_stream {
+  ka9q_stream_config cfg;
+  int N = 0, olen = 0, mdec = 0;
+  int bytes_per_samp = 4;
+  bool committed = false;
+  BigFftPlan fwd, p2048;
+  // device
+  void* d_ring = nullptr;
+  long long ring_cap = 0;
+  long long pushed = 0;        // samples pushed since stream start
+  long long block0 = 0;        // blocks computed since stream start
+  long long phase_block = 0;   // block counter used for LO phase / audio ring (advances in resident mode too)
+  float2 *d_spec = nullptr, *d_tmp0 = nullptr, *d_tmp1 = nullptr;
+  float* d_energy = nullptr;
+  float2* d_tw2048 = nullptr;
+  std::vector<ka9q_chan_params> chans;
+  std::vector<ChanParams> h_params;
+  std::vector<float> h_noise_gain;
+  ChanParams* d_params = nullptr;
+  ChanState* d_state = nullptr;
+  float2* d_resp = nullptr;
+  float2* d_audio_resp = nullptr;
+  float* d_audio_hist = nullptr;
+  int16_t* d_pcm = nullptr;
+  ChanStatus* d_status = nullptr;
+  float2* d_filt = nullptr;
+  float* d_windows = nullptr;
+  std::vector<float> betas;  // distinct Kaiser betas -> window table rows
+  int2 *d_work_fm = nullptr, *d_work_am = nullptr, *d_work_lin = nullptr;
+  int n_fm = 0, n_am = 0, n_lin = 0;
+  long long pcm_stride = 0;
+  // pinned staging
+  void* h_iq = nullptr;
+  int16_t* h_pcm = nullptr;
+  ChanStatus* h_status = nullptr;
+  // streams / events
+  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr, s_fm = nullptr, s_am = nullptr, s_lin = nullptr;
+  cudaEvent_t e_pushed = nullptr, e_fft0 = nullptr, e_fft1 = nullptr, e_chan1 = nullptr, e_fork = nullptr, e_am = nullptr,
+              e_lin = nullptr, e_fm = nullptr, e_comp_done[2] = {nullptr, nullptr}, e_fetched = nullptr;
+  int comp_parity = 0;
+  int last_nblocks = 0;
+  // NCCL (dlopen'ed)
+  void* nccl_comm = nullptr;
+};
+
+// ------------------------------------------------------------------ helpers
+
+static float default_headroom() { return (float)pow(10., -15. / 20); }  // main.c:117
+
+// dB2voltage(x) = powf(10., x/20.)  (dsp.h:37)
+static float dB2voltage_f(float x) { return powf(10., (x) / 20.); }
+
+static int window_index(ka9q_stream* s, float beta) {
+  for (size_t i = 0; i < s->betas.size(); i++)
+    if (s->betas[i] == beta) return (int)i;
+  s->betas.push_back(beta);
+  return (int)s->betas.size() - 1;
+}
+
+// normalised set_filter edges exactly as each demodulator computes them:
+//   FM:        low/dsamprate, dsamprate = (float)samprate / decimate            (fm.c:27,35)
+//   AM/linear: samptime*low,  samptime  = decimate / (float)samprate            (am.c:21,41; linear.c:29,81)
+static void normalised_edges(const ka9q_stream* s, const ka9q_chan_params& p, float* lo, float* hi) {
+  if (p.demod_type == KA9Q_FM_DEMOD) {
+    float const dsamprate = (float)s->cfg.samprate / s->cfg.decimate;
+    *lo = p.low / dsamprate;
+    *hi = p.high / dsamprate;
+  } else {
+    float const samptime = (float)s->cfg.decimate / (float)s->cfg.samprate;
+    *lo = samptime * p.low;
+    *hi = samptime * p.high;
+  }
+}
+
+static float response_gain(const ka9q_stream* s, const ka9q_chan_params& p) {
+  float gain = 1. / ((float)s->N);  // filter.c:518
+  if (p.demod_type == KA9Q_LINEAR_DEMOD && (p.flags & KA9Q_FLAG_ISB)) gain *= M_SQRT1_2;  // CROSS_CONJ, filter.c:520-521
+  return gain;
+}
+
+static int design_channels(ka9q_stream* s, int first, int count) {
+  // windows for every distinct beta
+  std::vector<DesignSpec> specs(count);
+  for (int i = 0; i < count; i++) {
+    const ka9q_chan_params& p = s->chans[first + i];
+    normalised_edges(s, p, &specs[i].low, &specs[i].high);
+    specs[i].gain = response_gain(s, p);
+    specs[i].window = window_index(s, p.kaiser_beta);
+  }
+  const int nb = (int)s->betas.size();
+  std::vector<float> win((size_t)nb * s->mdec);
+  for (int i = 0; i < nb; i++) kaiser_window_host(&win[(size_t)i * s->mdec], s->mdec, s->betas[i]);
+  if (s->d_windows) cudaFree(s->d_windows);
+  K9_CUDA(cudaMalloc(&s->d_windows, sizeof(float) * win.size()));
+  K9_CUDA(cudaMemcpy(s->d_windows, win.data(), sizeof(float) * win.size(), cudaMemcpyHostToDevice));
+  DesignSpec* d_specs = nullptr;
+  float2* d_work = nullptr;
+  float* d_ng = nullptr;
+  K9_CUDA(cudaMalloc(&d_specs, sizeof(DesignSpec) * count));
+  K9_CUDA(cudaMalloc(&d_work, sizeof(float2) * 2 * (size_t)count * NDEC));
+  K9_CUDA(cudaMalloc(&d_ng, sizeof(float) * count));
+  K9_CUDA(cudaMemcpy(d_specs, specs.data(), sizeof(DesignSpec) * count, cudaMemcpyHostToDevice));
+  int r = design_complex_batch(&s->p2048, NDEC, s->mdec, d_specs, count, s->d_windows, s->d_resp + (size_t)first * NDEC,
+                               d_work, s->s_comp);
+  // noise_gain = N * sum |H|^2, doubled for CROSS_CONJ (filter.c:472-497): computed unscaled, scaled on the host
+  if (r == 0) r = noise_gain_device(s->d_resp + (size_t)first * NDEC, NDEC, NDEC, count, 1.0f, d_ng, s->s_comp);
+  std::vector<float> ng(count);
+  if (r == 0) {
+    cudaError_t e = cudaMemcpyAsync(ng.data(), d_ng, sizeof(float) * count, cudaMemcpyDeviceToHost, s->s_comp);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->s_comp);
+    if (e != cudaSuccess) {
+      set_error("filter design failed: %s", cudaGetErrorString(e));
+      r = -1;
+    }
+  }
+  cudaFree(d_specs);
+  cudaFree(d_work);
+  cudaFree(d_ng);
+  if (r) {
+    if (!*get_error()) set_error("filter design launch failed");
+    return -1;
+  }
+  s->h_noise_gain.resize(s->chans.size());
+  for (int i = 0; i < count; i++) {
+    const ka9q_chan_params& p = s->chans[first + i];
+    const bool cc = p.demod_type == KA9Q_LINEAR_DEMOD && (p.flags & KA9Q_FLAG_ISB);
+    s->h_noise_gain[first + i] = cc ? 2 * s->N * ng[i] : s->N * ng[i];
+  }
+  return 0;
+}
+
+// FM post-detection audio responses (fm.c:39-66), one per distinct beta, stored full-length Hermitian
+static int design_audio(ka9q_stream* s, const std::vector<float>& audio_betas) {
+  const int na = (int)audio_betas.size();
+  if (na == 0) return 0;
+  const int AN = NDEC, AL = s->olen, AM = s->mdec;
+  float const dsamprate = (float)s->cfg.samprate / s->cfg.decimate;
+  float const filter_gain = 10. / AN;
+  const int nh = AN / 2 + 1;
+  std::vector<float2> half((size_t)na * nh, make_float2(0.f, 0.f));
+  std::vector<float> win((size_t)na * AM);
+  for (int a = 0; a < na; a++) {
+    for (int j = 0; j <= AN / 2; j++) {
+      float const f = (float)j * dsamprate / AN;
+      if (f >= 300 && f <= 6000) half[(size_t)a * nh + j].x = filter_gain * 300. / f;
+    }
+    kaiser_window_host(&win[(size_t)a * AM], AM, audio_betas[a]);
+  }
+  (void)AL;
+  float2 *d_half = nullptr, *d_work = nullptr;
+  float* d_win = nullptr;
+  K9_CUDA(cudaMalloc(&d_half, sizeof(float2) * half.size()));
+  K9_CUDA(cudaMalloc(&d_work, sizeof(float2) * 2 * (size_t)AN));
+  K9_CUDA(cudaMalloc(&d_win, sizeof(float) * win.size()));
+  K9_CUDA(cudaMalloc(&s->d_audio_resp, sizeof(float2) * (size_t)na * AN));
+  K9_CUDA(cudaMemcpy(d_half, half.data(), sizeof(float2) * half.size(), cudaMemcpyHostToDevice));
+  K9_CUDA(cudaMemcpy(d_win, win.data(), sizeof(float) * win.size(), cudaMemcpyHostToDevice));
+  int r = 0;
+  for (int a = 0; a < na && r == 0; a++)
+    r = window_rfilter_device(&s->p2048, AM, d_half + (size_t)a * nh, s->d_audio_resp + (size_t)a * AN, 1,
+                              d_win + (size_t)a * AM, d_work, s->s_comp);
+  cudaError_t e = cudaStreamSynchronize(s->s_comp);
+  cudaFree(d_half);
+  cudaFree(d_work);
+  cudaFree(d_win);
+  K9_CHECK(r == 0 && e == cudaSuccess, "audio response design failed");
+  return 0;
+}
+
+// ------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+const char* ka9q_last_error(void) { return k9::get_error(); }
+const char* ka9q_version(void) { return "ka9q_b200 0.1 (sm_100a)"; }
+
+int ka9q_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int ka9q_stream_create(ka9q_stream** out, const ka9q_stream_config* cfg) {
+  K9_CHECK(out && cfg, "null argument");
+  *out = nullptr;
+  K9_CHECK(cfg->samprate > 0 && cfg->L > 0 && cfg->M > 0 && cfg->decimate > 0, "bad geometry");
+  const int N = cfg->L + cfg->M - 1;
+  K9_CHECK(N % cfg->decimate == 0, "FFT size %d is not divisible by decimation ratio %d (filter.c:106-107)", N,
+           cfg->decimate);
+  K9_CHECK(N / cfg->decimate == NDEC, "N/decimate must be %d for the fused channel kernels (got %d)", NDEC,
+           N / cfg->decimate);
+  K9_CHECK(cfg->L % cfg->decimate == 0, "L must be a multiple of decimate");
+  K9_CHECK(cfg->iq_format == KA9Q_IQ_S16 || cfg->iq_format == KA9Q_IQ_S8, "bad iq_format");
+  K9_CHECK(cfg->max_blocks >= 1, "max_blocks must be >= 1");
+  K9_CHECK(ka9q_device_count() > cfg->device && cfg->device >= 0,
+           "CUDA device %d not available (no CPU fallback exists)", cfg->device);
+  K9_CUDA(cudaSetDevice(cfg->device));
+  ka9q_stream* s = new ka9q_stream();
+  s->cfg = *cfg;
+  s->N = N;
+  s->olen = cfg->L / cfg->decimate;
+  s->mdec = (cfg->M - 1) / cfg->decimate + 1;  // filter.c:514
+  s->bytes_per_samp = cfg->iq_format == KA9Q_IQ_S16 ? 4 : 2;
+  if (bigfft_plan_create(&s->fwd, N) != 0) {
+    set_error("forward FFT size %d has no supported factorisation (2^a 3^b 5^c with pass sizes 16..400)", N);
+    delete s;
+    return -1;
+  }
+  if (bigfft_plan_create(&s->p2048, NDEC) != 0) {
+    set_error("internal: 2048-point plan");
+    delete s;
+    return -1;
+  }
+  *out = s;
+  return 0;
+}
+
+int ka9q_stream_add_channel(ka9q_stream* s, const ka9q_chan_params* p) {
+  K9_CHECK(s && p, "null argument");
+  K9_CHECK(!s->committed, "channels must be added before commit");
+  K9_CHECK(p->demod_type >= 0 && p->demod_type <= 2, "bad demod_type");
+  K9_CHECK(!(p->flags & (KA9Q_FLAG_PLL | KA9Q_FLAG_SQUARE)),
+           "PLL / squaring carrier tracking (linear.c:129-246) is not implemented in this build");
+  K9_CHECK(!isnan(p->low) && !isnan(p->high), "filter edges must be set (set_filter returns -1 on NAN, filter.c:504)");
+  ka9q_chan_params q = *p;
+  if (q.low > q.high) std::swap(q.low, q.high);  // radio.c:347-353
+  if (isnan(q.headroom)) q.headroom = default_headroom();
+  if (q.channels != 1 && q.channels != 2) q.channels = (q.demod_type == KA9Q_LINEAR_DEMOD) ? 2 : 1;
+  if (q.demod_type != KA9Q_LINEAR_DEMOD) q.channels = 1;  // fm.c:30, am.c:36
+  q.bin %= s->N;
+  if (q.bin < 0) q.bin += s->N;
+  s->chans.push_back(q);
+  return (int)s->chans.size() - 1;
+}
+
+int ka9q_stream_commit(ka9q_stream* s) {
+  K9_CHECK(s, "null argument");
+  K9_CHECK(!s->committed, "already committed");
+  K9_CHECK(!s->chans.empty(), "no channels");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  const int K = (int)s->chans.size();
+  const int B = s->cfg.max_blocks;
+  const int L = s->cfg.L, M = s->cfg.M, N = s->N;
+  K9_CUDA(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
+  K9_CUDA(cudaStreamCreateWithFlags(&s->s_comp, cudaStreamNonBlocking));
+  K9_CUDA(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
+  K9_CUDA(cudaStreamCreateWithFlags(&s->s_fm, cudaStreamNonBlocking));
+  K9_CUDA(cudaStreamCreateWithFlags(&s->s_am, cudaStreamNonBlocking));
+  K9_CUDA(cudaStreamCreateWithFlags(&s->s_lin, cudaStreamNonBlocking));
+  cudaEvent_t* evs[] = {&s->e_pushed, &s->e_fork, &s->e_am, &s->e_lin, &s->e_fm, &s->e_comp_done[0], &s->e_comp_done[1],
+                        &s->e_fetched};
+  for (auto e : evs) K9_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  K9_CUDA(cudaEventCreate(&s->e_fft0));
+  K9_CUDA(cudaEventCreate(&s->e_fft1));
+  K9_CUDA(cudaEventCreate(&s->e_chan1));
+
+  // I/Q ring: history + two batches, so the copy of batch k+1 may overlap the compute of batch k
+  s->ring_cap = (long long)(M - 1) + 2LL * B * L;
+  K9_CUDA(cudaMalloc(&s->d_ring, (size_t)s->ring_cap * s->bytes_per_samp));
+  K9_CUDA(cudaMemset(s->d_ring, 0, (size_t)s->ring_cap * s->bytes_per_samp));  // zero history (filter.c:77)
+  K9_CUDA(cudaMalloc(&s->d_spec, sizeof(float2) * (size_t)B * N));
+  K9_CUDA(cudaMalloc(&s->d_tmp0, sizeof(float2) * (size_t)B * N));
+  if (s->fwd.npass >= 3) K9_CUDA(cudaMalloc(&s->d_tmp1, sizeof(float2) * (size_t)B * N));
+  K9_CUDA(cudaMalloc(&s->d_energy, sizeof(float) * B));
+  {
+    std::vector<float2> tw(NDEC);
+    for (int a = 0; a < NDEC; a++) {
+      double ang = -2.0 * M_PI * a / NDEC;
+      tw[a] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    K9_CUDA(cudaMalloc(&s->d_tw2048, sizeof(float2) * NDEC));
+    K9_CUDA(cudaMemcpy(s->d_tw2048, tw.data(), sizeof(float2) * NDEC, cudaMemcpyHostToDevice));
+  }
+  // per-channel arrays
+  K9_CUDA(cudaMalloc(&s->d_resp, sizeof(float2) * (size_t)K * NDEC));
+  K9_CUDA(cudaMalloc(&s->d_params, sizeof(ChanParams) * K));
+  K9_CUDA(cudaMalloc(&s->d_state, sizeof(ChanState) * K));
+  K9_CUDA(cudaMalloc(&s->d_status, sizeof(ChanStatus) * (size_t)B * K));
+  K9_CUDA(cudaMemset(s->d_status, 0, sizeof(ChanStatus) * (size_t)B * K));
+
+  // parameter blocks, PCM layout, work lists
+  s->h_params.resize(K);
+  std::vector<ChanState> st(K);
+  memset(st.data(), 0, sizeof(ChanState) * K);
+  std::vector<float> audio_betas;
+  std::map<int, std::vector<int>> fm_groups;  // audio slot -> channels
+  std::vector<int2> w_fm, w_am, w_lin;
+  long long off = 0;
+  bool any_fm = false;
+  float const dsamprate = (float)s->cfg.samprate / s->cfg.decimate;
+  for (int c = 0; c < K; c++) {
+    const ka9q_chan_params& p = s->chans[c];
+    ChanParams& P = s->h_params[c];
+    memset(&P, 0, sizeof(P));
+    P.bin = p.bin;
+    P.demod = p.demod_type;
+    P.flags = p.flags;
+    P.channels = p.channels;
+    P.pcm_off = (int)off;
+    off += (long long)s->olen * p.channels;
+    P.headroom = p.headroom;
+    P.audio_slot = -1;
+    float const samptime = (float)s->cfg.decimate / (float)s->cfg.samprate;
+    if (p.demod_type == KA9Q_FM_DEMOD) {
+      any_fm = true;
+      // fm.c:86: (headroom * M_1_PI * dsamprate) / fabsf(low - high), evaluated in double, stored to float
+      P.fm_gain = (p.headroom * M_1_PI * dsamprate) / fabsf(p.low - p.high);
+      st[c].fm_state = make_float2(1.f, 0.f);  // fm.c:26
+      if (!(p.flags & KA9Q_FLAG_FLAT)) {
+        int slot = -1;
+        for (size_t i = 0; i < audio_betas.size(); i++)
+          if (audio_betas[i] == p.kaiser_beta) slot = (int)i;
+        if (slot < 0) {
+          audio_betas.push_back(p.kaiser_beta);
+          slot = (int)audio_betas.size() - 1;
+        }
+        P.audio_slot = slot;
+        fm_groups[slot].push_back(c);
+      } else {
+        w_fm.push_back(make_int2(c, -1));
+      }
+    } else {
+      P.recovery_factor = dB2voltage_f(p.recovery_rate * samptime);  // am.c:27, linear.c:33
+      P.hangmax = (int)(p.hangtime / samptime);                       // am.c:29, linear.c:37
+      if (p.demod_type == KA9Q_AM_DEMOD) {
+        st[c].agc_gain = dB2voltage_f(80.);  // am.c:30
+        w_am.push_back(make_int2(c, -1));
+      } else {
+        st[c].agc_gain = dB2voltage_f(100.0);  // linear.c:39
+        // radio.c:313: shift * decimate / samprate, cycles per output sample
+        P.shift_cycles = (p.shift == 0) ? 0.0 : (double)p.shift * s->cfg.decimate / (double)s->cfg.samprate;
+        w_lin.push_back(make_int2(c, -1));
+      }
+    }
+  }
+  for (auto& g : fm_groups) {
+    const std::vector<int>& v = g.second;
+    for (size_t i = 0; i < v.size(); i += 2) w_fm.push_back(make_int2(v[i], i + 1 < v.size() ? v[i + 1] : -1));
+  }
+  s->pcm_stride = off;
+  s->n_fm = (int)w_fm.size();
+  s->n_am = (int)w_am.size();
+  s->n_lin = (int)w_lin.size();
+  auto upload_work = [&](const std::vector<int2>& w, int2** d) -> int {
+    if (w.empty()) return 0;
+    K9_CUDA(cudaMalloc(d, sizeof(int2) * w.size()));
+    K9_CUDA(cudaMemcpy(*d, w.data(), sizeof(int2) * w.size(), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  if (upload_work(w_fm, &s->d_work_fm) || upload_work(w_am, &s->d_work_am) || upload_work(w_lin, &s->d_work_lin)) return -1;
+  K9_CUDA(cudaMemcpy(s->d_params, s->h_params.data(), sizeof(ChanParams) * K, cudaMemcpyHostToDevice));
+  K9_CUDA(cudaMemcpy(s->d_state, st.data(), sizeof(ChanState) * K, cudaMemcpyHostToDevice));
+  if (any_fm) {
+    K9_CUDA(cudaMalloc(&s->d_audio_hist, sizeof(float) * (size_t)K * NDEC));
+    K9_CUDA(cudaMemset(s->d_audio_hist, 0, sizeof(float) * (size_t)K * NDEC));  // zero history (filter.c:87)
+  }
+  K9_CUDA(cudaMalloc(&s->d_pcm, sizeof(int16_t) * (size_t)B * s->pcm_stride));
+  K9_CUDA(cudaMemset(s->d_pcm, 0, sizeof(int16_t) * (size_t)B * s->pcm_stride));
+  if (s->cfg.capture_filter_output) K9_CUDA(cudaMalloc(&s->d_filt, sizeof(float2) * (size_t)B * K * s->olen));
+  // pinned staging
+  K9_CUDA(cudaHostAlloc(&s->h_iq, (size_t)B * L * s->bytes_per_samp, cudaHostAllocDefault));
+  K9_CUDA(cudaHostAlloc((void**)&s->h_pcm, sizeof(int16_t) * (size_t)B * s->pcm_stride, cudaHostAllocDefault));
+  K9_CUDA(cudaHostAlloc((void**)&s->h_status, sizeof(ChanStatus) * (size_t)B * K, cudaHostAllocDefault));
+
+  if (design_channels(s, 0, K)) return -1;
+  if (design_audio(s, audio_betas)) return -1;
+  s->committed = true;
+  return 0;
+}
+
+int ka9q_stream_set_filter(ka9q_stream* s, int chan, float low, float high, float kaiser_beta) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  K9_CHECK(chan >= 0 && chan < (int)s->chans.size(), "bad channel");
+  K9_CHECK(!isnan(low) && !isnan(high), "NAN edge (filter.c:504-505)");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  ka9q_chan_params& p = s->chans[chan];
+  if (p.demod_type == KA9Q_FM_DEMOD && !(p.flags & KA9Q_FLAG_FLAT))
+    K9_CHECK(kaiser_beta == p.kaiser_beta, "changing kaiser_beta of a de-emphasised FM channel after commit is unsupported");
+  p.low = std::min(low, high);
+  p.high = std::max(low, high);
+  p.kaiser_beta = kaiser_beta;
+  K9_CUDA(cudaStreamSynchronize(s->s_comp));
+  if (design_channels(s, chan, 1)) return -1;
+  if (p.demod_type == KA9Q_FM_DEMOD) {
+    float const dsamprate = (float)s->cfg.samprate / s->cfg.decimate;
+    s->h_params[chan].fm_gain = (p.headroom * M_1_PI * dsamprate) / fabsf(p.low - p.high);
+    K9_CUDA(cudaMemcpy(s->d_params + chan, &s->h_params[chan], sizeof(ChanParams), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int ka9q_stream_num_channels(const ka9q_stream* s) { return s ? (int)s->chans.size() : -1; }
+long long ka9q_stream_pcm_stride(const ka9q_stream* s) { return s ? s->pcm_stride : -1; }
+int ka9q_stream_pcm_offset(const ka9q_stream* s, int chan) {
+  if (!s || !s->committed || chan < 0 || chan >= (int)s->chans.size()) return -1;
+  return s->h_params[chan].pcm_off;
+}
+int ka9q_stream_olen(const ka9q_stream* s) { return s ? s->olen : -1; }
+int ka9q_stream_fft_size(const ka9q_stream* s) { return s ? s->N : -1; }
+int ka9q_stream_launches_per_call(const ka9q_stream* s) {
+  if (!s) return -1;
+  return s->fwd.npass + (s->n_fm ? 1 : 0) + (s->n_am ? 1 : 0) + (s->n_lin ? 1 : 0);
+}
+
+int ka9q_stream_push(ka9q_stream* s, const void* iq, int nblocks) {
+  K9_CHECK(s && s->committed && iq, "bad argument");
+  K9_CHECK(nblocks >= 1 && nblocks <= s->cfg.max_blocks, "nblocks out of range");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  const long long n = (long long)nblocks * s->cfg.L;
+  // the region about to be overwritten was last read by the compute issued two calls ago
+  K9_CHECK(s->pushed + n - s->block0 * (long long)s->cfg.L <= 2LL * s->cfg.max_blocks * s->cfg.L,
+           "push would overwrite samples that have not been computed yet");
+  K9_CUDA(cudaStreamWaitEvent(s->s_in, s->e_comp_done[s->comp_parity ^ 1], 0));
+  long long pos = (s->pushed + (s->cfg.M - 1)) % s->ring_cap;
+  long long done = 0;
+  while (done < n) {
+    long long chunk = std::min(n - done, s->ring_cap - pos);
+    K9_CUDA(cudaMemcpyAsync((char*)s->d_ring + pos * s->bytes_per_samp, (const char*)iq + done * s->bytes_per_samp,
+                            (size_t)chunk * s->bytes_per_samp, cudaMemcpyHostToDevice, s->s_in));
+    done += chunk;
+    pos = (pos + chunk) % s->ring_cap;
+  }
+  s->pushed += n;
+  K9_CUDA(cudaEventRecord(s->e_pushed, s->s_in));
+  return 0;
+}
+
+static void fill_launch(ka9q_stream* s, ChanLaunch& a, int nblocks) {
+  memset(&a, 0, sizeof(a));
+  a.spec = s->d_spec;
+  a.spec_stride = s->N;
+  a.N = s->N;
+  a.L = s->cfg.L;
+  a.M = s->cfg.M;
+  a.olen = s->olen;
+  a.dsamprate = (float)s->cfg.samprate / s->cfg.decimate;
+  a.nblocks = nblocks;
+  a.block0 = s->phase_block;
+  a.tw2048 = s->d_tw2048;
+  a.params = s->d_params;
+  a.state = s->d_state;
+  a.resp = s->d_resp;
+  a.audio_resp = s->d_audio_resp;
+  a.audio_hist = s->d_audio_hist;
+  a.pcm = s->d_pcm;
+  a.pcm_stride = s->pcm_stride;
+  a.status = s->d_status;
+  a.nchan_total = (int)s->chans.size();
+  a.filt_dbg = s->d_filt;
+}
+
+static int issue_fft(ka9q_stream* s, int nblocks, long long first_block) {
+  BigFftIn in;
+  in.in_mode = s->cfg.iq_format == KA9Q_IQ_S16 ? IN_RING_S16 : IN_RING_S8;
+  in.in = s->d_ring;
+  in.ring_cap = s->ring_cap;
+  in.ring_off = (first_block * (long long)s->cfg.L) % s->ring_cap;
+  in.ring_step = s->cfg.L;
+  in.scale = s->cfg.iq_format == KA9Q_IQ_S16 ? (float)(1. / 32767) : (float)(1. / 127);  // radio.c:38-39
+  in.gain = s->cfg.gain_factor;
+  in.stat_from = s->cfg.M - 1;
+  in.energy = s->d_energy;
+  K9_CUDA(cudaMemsetAsync(s->d_energy, 0, sizeof(float) * nblocks, s->s_comp));
+  K9_CUDA(cudaEventRecord(s->e_fft0, s->s_comp));
+  if (bigfft_exec(&s->fwd, in, s->d_spec, s->N, s->d_tmp0, s->d_tmp1, nblocks, -1, s->s_comp)) {
+    set_error("forward FFT launch failed");
+    return -1;
+  }
+  K9_CUDA(cudaEventRecord(s->e_fft1, s->s_comp));
+  return 0;
+}
+
+static int issue_channels(ka9q_stream* s, int nblocks) {
+  ChanLaunch a;
+  fill_launch(s, a, nblocks);
+  // the three demodulator families run concurrently on sibling streams
+  K9_CUDA(cudaEventRecord(s->e_fork, s->s_comp));
+  if (s->n_am) {
+    K9_CUDA(cudaStreamWaitEvent(s->s_am, s->e_fork, 0));
+    a.work = s->d_work_am;
+    a.nwork = s->n_am;
+    K9_CHECK(launch_am(a, s->s_am) == 0, "am kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    K9_CUDA(cudaEventRecord(s->e_am, s->s_am));
+  }
+  if (s->n_lin) {
+    K9_CUDA(cudaStreamWaitEvent(s->s_lin, s->e_fork, 0));
+    a.work = s->d_work_lin;
+    a.nwork = s->n_lin;
+    K9_CHECK(launch_linear(a, s->s_lin) == 0, "linear kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    K9_CUDA(cudaEventRecord(s->e_lin, s->s_lin));
+  }
+  if (s->n_fm) {
+    a.work = s->d_work_fm;
+    a.nwork = s->n_fm;
+    K9_CHECK(launch_fm(a, s->s_comp) == 0, "fm kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (s->n_am) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_am, 0));
+  if (s->n_lin) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_lin, 0));
+  K9_CUDA(cudaEventRecord(s->e_chan1, s->s_comp));
+  s->phase_block += nblocks;
+  return 0;
+}
+
+static int compute_impl(ka9q_stream* s, int nblocks, bool resident, bool do_fft, bool do_chan) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  K9_CHECK(nblocks >= 1 && nblocks <= s->cfg.max_blocks, "nblocks out of range");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  long long first_block;
+  if (resident) {
+    first_block = s->pushed / s->cfg.L - nblocks;
+    K9_CHECK(first_block >= 0, "not enough samples resident in the ring");
+    // resident re-runs keep the true block index for the ring window but a running index for LO phase/audio ring
+    if (s->phase_block < first_block) s->phase_block = first_block;
+  } else {
+    first_block = s->block0;
+    K9_CHECK((first_block + nblocks) * (long long)s->cfg.L <= s->pushed, "compute ahead of pushed samples");
+  }
+  K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_pushed, 0));
+  K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_fetched, 0));  // previous results must have left d_pcm
+  if (do_fft && issue_fft(s, nblocks, first_block)) return -1;
+  if (do_chan && issue_channels(s, nblocks)) return -1;
+  if (do_chan || !do_fft) {
+    s->comp_parity ^= 1;
+    K9_CUDA(cudaEventRecord(s->e_comp_done[s->comp_parity], s->s_comp));
+    if (!resident) s->block0 += nblocks;
+    s->last_nblocks = nblocks;
+  }
+  return 0;
+}
+
+int ka9q_stream_compute(ka9q_stream* s, int nblocks) { return compute_impl(s, nblocks, false, true, true); }
+int ka9q_stream_compute_resident(ka9q_stream* s, int nblocks) { return compute_impl(s, nblocks, true, true, true); }
+int ka9q_stream_compute_fft_only(ka9q_stream* s, int nblocks) { return compute_impl(s, nblocks, true, true, false); }
+int ka9q_stream_compute_channels_only(ka9q_stream* s, int nblocks) { return compute_impl(s, nblocks, true, false, true); }
+
+int ka9q_stream_fetch(ka9q_stream* s, int nblocks, int16_t* pcm, ka9q_chan_status* status) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  K9_CHECK(nblocks >= 1 && nblocks <= s->cfg.max_blocks, "nblocks out of range");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  K9_CUDA(cudaStreamWaitEvent(s->s_out, s->e_comp_done[s->comp_parity], 0));
+  if (pcm)
+    K9_CUDA(cudaMemcpyAsync(pcm, s->d_pcm, sizeof(int16_t) * (size_t)nblocks * s->pcm_stride, cudaMemcpyDeviceToHost,
+                            s->s_out));
+  if (status)
+    K9_CUDA(cudaMemcpyAsync(status, s->d_status, sizeof(ChanStatus) * (size_t)nblocks * s->chans.size(),
+                            cudaMemcpyDeviceToHost, s->s_out));
+  K9_CUDA(cudaEventRecord(s->e_fetched, s->s_out));
+  return 0;
+}
+
+int ka9q_stream_sync(ka9q_stream* s) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  K9_CUDA(cudaStreamSynchronize(s->s_in));
+  K9_CUDA(cudaStreamSynchronize(s->s_comp));
+  K9_CUDA(cudaStreamSynchronize(s->s_am));
+  K9_CUDA(cudaStreamSynchronize(s->s_lin));
+  K9_CUDA(cudaStreamSynchronize(s->s_out));
+  return 0;
+}
+
+int ka9q_stream_process(ka9q_stream* s, const void* iq, int nblocks, int16_t* pcm, ka9q_chan_status* status) {
+  static_assert(sizeof(ka9q_chan_status) == sizeof(ChanStatus), "status layout");
+  if (ka9q_stream_push(s, iq, nblocks)) return -1;
+  if (ka9q_stream_compute(s, nblocks)) return -1;
+  if (ka9q_stream_fetch(s, nblocks, pcm, status)) return -1;
+  return ka9q_stream_sync(s);
+}
+
+int ka9q_stream_last_timing(ka9q_stream* s, float* total_ms, float* fft_ms, float* chan_ms) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  float f = 0, c = 0;
+  K9_CUDA(cudaEventElapsedTime(&f, s->e_fft0, s->e_fft1));
+  K9_CUDA(cudaEventElapsedTime(&c, s->e_fft1, s->e_chan1));
+  if (fft_ms) *fft_ms = f;
+  if (chan_ms) *chan_ms = c;
+  if (total_ms) *total_ms = f + c;
+  return 0;
+}
+
+int ka9q_stream_spectrum_ptr(ka9q_stream* s, void** dev_ptr, long long* bytes_per_block) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  if (dev_ptr) *dev_ptr = s->d_spec;
+  if (bytes_per_block) *bytes_per_block = (long long)sizeof(float2) * s->N;
+  return 0;
+}
+
+int ka9q_stream_get_response(ka9q_stream* s, int chan, void* out2048, float* noise_gain) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  K9_CHECK(chan >= 0 && chan < (int)s->chans.size(), "bad channel");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  if (out2048)
+    K9_CUDA(cudaMemcpy(out2048, s->d_resp + (size_t)chan * NDEC, sizeof(float2) * NDEC, cudaMemcpyDeviceToHost));
+  if (noise_gain) *noise_gain = s->h_noise_gain[chan];
+  return 0;
+}
+
+int ka9q_stream_get_filter_output(ka9q_stream* s, int chan, int nblocks, void* out) {
+  K9_CHECK(s && s->committed && s->d_filt, "filter-output capture not enabled");
+  K9_CHECK(chan >= 0 && chan < (int)s->chans.size() && nblocks >= 1 && nblocks <= s->cfg.max_blocks, "bad argument");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  const int K = (int)s->chans.size();
+  K9_CUDA(cudaMemcpy2D(out, sizeof(float2) * s->olen, s->d_filt + (size_t)chan * s->olen, sizeof(float2) * (size_t)K * s->olen,
+                       sizeof(float2) * s->olen, nblocks, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ka9q_stream_get_spectrum(ka9q_stream* s, int block, void* outN) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  K9_CHECK(block >= 0 && block < s->cfg.max_blocks, "bad block");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  K9_CUDA(cudaMemcpy(outN, s->d_spec + (size_t)block * s->N, sizeof(float2) * s->N, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ka9q_stream_get_if_energy(ka9q_stream* s, int nblocks, float* energy) {
+  K9_CHECK(s && s->committed && energy, "bad argument");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  K9_CUDA(cudaMemcpy(energy, s->d_energy, sizeof(float) * nblocks, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ka9q_stream_destroy(ka9q_stream* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->cfg.device);
+  cudaDeviceSynchronize();
+  bigfft_plan_destroy(&s->fwd);
+  bigfft_plan_destroy(&s->p2048);
+  void* dev[] = {s->d_ring, s->d_spec, s->d_tmp0, s->d_tmp1, s->d_energy, s->d_tw2048, s->d_params, s->d_state, s->d_resp,
+                 s->d_audio_resp, s->d_audio_hist, s->d_pcm, s->d_status, s->d_filt, s->d_windows, s->d_work_fm,
+                 s->d_work_am, s->d_work_lin};
+  for (void* p : dev)
+    if (p) cudaFree(p);
+  if (s->h_iq) cudaFreeHost(s->h_iq);
+  if (s->h_pcm) cudaFreeHost(s->h_pcm);
+  if (s->h_status) cudaFreeHost(s->h_status);
+  cudaStream_t sts[] = {s->s_in, s->s_comp, s->s_out, s->s_fm, s->s_am, s->s_lin};
+  for (auto st : sts)
+    if (st) cudaStreamDestroy(st);
+  cudaEvent_t evs[] = {s->e_pushed, s->e_fft0, s->e_fft1, s->e_chan1, s->e_fork, s->e_am, s->e_lin, s->e_fm,
+                       s->e_comp_done[0], s->e_comp_done[1], s->e_fetched};
+  for (auto e : evs)
+    if (e) cudaEventDestroy(e);
+  delete s;
+  return 0;
+}
+
+
+// ------------------------------------------------------------------ pinned host memory
+
+void* ka9q_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 64, cudaHostAllocDefault) != cudaSuccess) {
+    set_error("ka9q_host_alloc: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+void ka9q_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ NCCL spectrum broadcast (libnccl dlopen'ed)
+// The only inter-GPU exchange of the path: the rank that ingested the block broadcasts N*8 bytes of
+// spectrum per block; channels never move.
+
+typedef struct ncclComm* k9_ncclComm_t;
+typedef struct {
+  char internal[128];
+} k9_ncclUniqueId;
+static int (*p_ncclGetUniqueId)(k9_ncclUniqueId*);
+static int (*p_ncclCommInitRank)(k9_ncclComm_t*, int, k9_ncclUniqueId, int);
+static int (*p_ncclBroadcast)(const void*, void*, size_t, int, int, k9_ncclComm_t, cudaStream_t);
+static int (*p_ncclCommDestroy)(k9_ncclComm_t);
+static const char* (*p_ncclGetErrorString)(int);
+
+static int load_nccl() {
+  static int state = 0;  // 0 untried, 1 ok, -1 failed
+  if (state) return state > 0 ? 0 : -1;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    state = -1;
+    set_error("cannot load libnccl.so.2: %s", dlerror());
+    return -1;
+  }
+  p_ncclGetUniqueId = (int (*)(k9_ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+  p_ncclCommInitRank = (int (*)(k9_ncclComm_t*, int, k9_ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+  p_ncclBroadcast = (int (*)(const void*, void*, size_t, int, int, k9_ncclComm_t, cudaStream_t))dlsym(h, "ncclBroadcast");
+  p_ncclCommDestroy = (int (*)(k9_ncclComm_t))dlsym(h, "ncclCommDestroy");
+  p_ncclGetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!p_ncclGetUniqueId || !p_ncclCommInitRank || !p_ncclBroadcast) {
+    state = -1;
+    set_error("libnccl.so.2 lacks required symbols");
+    return -1;
+  }
+  state = 1;
+  return 0;
+}
+
+int ka9q_nccl_unique_id(void* id128) {
+  K9_CHECK(id128, "null argument");
+  if (load_nccl()) return -1;
+  k9_ncclUniqueId id;
+  int r = p_ncclGetUniqueId(&id);
+  K9_CHECK(r == 0, "ncclGetUniqueId: %s", p_ncclGetErrorString ? p_ncclGetErrorString(r) : "error");
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int ka9q_stream_nccl_init(ka9q_stream* s, const void* id128, int rank, int nranks) {
+  K9_CHECK(s && s->committed && id128, "bad argument");
+  if (load_nccl()) return -1;
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  k9_ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  k9_ncclComm_t comm = nullptr;
+  int r = p_ncclCommInitRank(&comm, nranks, id, rank);
+  K9_CHECK(r == 0, "ncclCommInitRank: %s", p_ncclGetErrorString ? p_ncclGetErrorString(r) : "error");
+  s->nccl_comm = comm;
+  return 0;
+}
+
+int ka9q_stream_nccl_broadcast_spectrum(ka9q_stream* s, int nblocks, int root) {
+  K9_CHECK(s && s->committed && s->nccl_comm, "NCCL communicator not initialised");
+  K9_CHECK(nblocks >= 1 && nblocks <= s->cfg.max_blocks, "nblocks out of range");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  // float32 count: 2 floats per bin; ordered on the compute stream right after the forward FFT
+  const size_t count = (size_t)2 * s->N * nblocks;
+  int r = p_ncclBroadcast(s->d_spec, s->d_spec, count, /*ncclFloat32=*/7, root, (k9_ncclComm_t)s->nccl_comm, s->s_comp);
+  K9_CHECK(r == 0, "ncclBroadcast: %s", p_ncclGetErrorString ? p_ncclGetErrorString(r) : "error");
+  return 0;
+}
+
+// ------------------------------------------------------------------ generic FFT on host buffers (tests / cross-checks)
+
+int ka9q_fft_plan_describe(int n, int* sizes) {
+  int R1[4], R2[4];
+  int np = bigfft_factorize(n, R1, R2);
+  if (np < 0) return -1;
+  for (int i = 0; i < np; i++)
+    if (sizes) sizes[i] = R1[i] * R2[i];
+  return np;
+}
+
+int ka9q_fft_c2c(int device, int n, int batch, int sign, const void* in, void* out) {
+  K9_CHECK(in && out && n >= 16 && batch >= 1, "bad argument");
+  K9_CHECK(ka9q_device_count() > device && device >= 0, "CUDA device %d not available (no CPU fallback exists)", device);
+  K9_CUDA(cudaSetDevice(device));
+  BigFftPlan plan;
+  K9_CHECK(bigfft_plan_create(&plan, n) == 0, "FFT size %d unsupported", n);
+  float2 *d_in = nullptr, *d_out = nullptr, *d_t0 = nullptr, *d_t1 = nullptr;
+  const size_t bytes = sizeof(float2) * (size_t)n * batch;
+  K9_CUDA(cudaMalloc(&d_in, bytes));
+  K9_CUDA(cudaMalloc(&d_out, bytes));
+  K9_CUDA(cudaMalloc(&d_t0, bytes));
+  K9_CUDA(cudaMalloc(&d_t1, bytes));
+  K9_CUDA(cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice));
+  BigFftIn bi;
+  bi.in = d_in;
+  bi.in_batch_stride = n;
+  int r = bigfft_exec(&plan, bi, d_out, n, d_t0, d_t1, batch, sign, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (r == 0 && e == cudaSuccess) e = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  cudaFree(d_t0);
+  cudaFree(d_t1);
+  bigfft_plan_destroy(&plan);
+  K9_CHECK(r == 0 && e == cudaSuccess, "fft failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"
