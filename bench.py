@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: channel·MS/s demodulated on the cfg5 workload (8192 NBFM channels per GPU on a
+61.44 MS/s complex int16 stream), device-resident (`value`) and end to end through the C ABI with host buffers (`e2e`),
+plus the roofline of the dominant kernel and the reference's CPU path timed on this box's host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg5] [--blocks B]
+
+One "step" = one pass of the hot path over one batch of B consecutive 20 ms blocks of synthetic I/Q
+(forward FFT once per block + every channel: bin rotation, response multiply, inverse FFT, overlap discard, FM
+demodulation, de-emphasis filter, int16 PCM).
+Multi-GPU (torchrun, one rank per GPU): weak scaling — every rank runs the full channel plan; rank 0 ingests the
+stream, runs the forward FFT and broadcasts the spectrum with NCCL (the only exchange of the path).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "channel·MS/s demodulated"
+UNIT = "channel·MS/s"
+
+
+def make_plan(name: str, nchan: int | None):
+    from ka9q_sdr_b200 import workloads
+    if name == "cfg5":
+        return workloads.cfg5(nchan or 8192)
+    if name == "cfg4":
+        return workloads.cfg4(nchan or 1024)
+    return workloads.CONFIGS[name]()
+
+
+def make_input(plan, nblocks: int) -> np.ndarray:
+    from ka9q_sdr_b200 import synth
+    if len(plan.channels) > 128:
+        fm_bins = [c.bin for c in plan.channels]
+        return synth.comb_spectrum_iq(plan.samprate, nblocks, fm_bins, plan.seed, plan.amplitude, plan.sigma,
+                                      deviation=plan.deviation)["iq"]
+    return synth.multi_channel(plan.samprate, nblocks, [c.bin for c in plan.channels], [c.mode for c in plan.channels],
+                               plan.seed, plan.amplitude, plan.sigma, deviation=plan.deviation)["iq"]
+
+
+def algorithmic_bytes(plan, nblocks: int):
+    """(per-step bytes of the channel kernels, per-step bytes of ingest + forward FFT)"""
+    from ka9q_sdr_b200 import modes, workloads
+    olen = plan.L // plan.D
+    chan = 0
+    for c in plan.channels:
+        m = modes.get_mode(c.mode)
+        pcm_ch = m.channels if m.demod_type == modes.LINEAR_DEMOD else 1
+        chan += workloads.channel_block_bytes(m.demod_type, pcm_ch, olen, m.flat)
+    return chan * nblocks, workloads.stream_block_bytes(plan.L, plan.N) * nblocks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+                 "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        try:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            sm, smax, reasons = [], [], set()
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                       "samples": len(sm)}
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+
+def run_reference(args, plan, emit=True):
+    """The reference's own CPU implementation (oracle/_ref: verbatim reference C, one `radio`-equivalent chain per
+    channel = per-sample LO + own N-point forward FFT + inverse FFT + demodulator), one channel per host thread."""
+    from concurrent.futures import ThreadPoolExecutor
+    from ka9q_sdr_b200 import modes
+    from oracle import refbind as R
+    cores = os.cpu_count() or 1
+    if not R.available():
+        line = {"impl": "reference", "unavailable": "oracle/_ref/libka9q_ref.so not built (needs /root/reference at build time)"}
+        if emit:
+            print(json.dumps(line))
+        return line
+    R.lib()
+    backend_ok = R.set_fft_backend("auto")
+    backend = R.fft_backend()
+    R.load_modes(modes.MODES.values())
+    nthreads = min(cores, len(plan.channels))
+    # bounded sample: `nthreads` channels x nb blocks per step
+    per_chan_block_cost = plan.N / 2621440 * 0.06 + 0.0007      # rough seconds, only used to size the sample
+    nb = int(max(2, min(16, round(1.0 / per_chan_block_cost))))
+    if args.ref_blocks:
+        nb = args.ref_blocks
+    iq = make_input(plan, nb)
+    chans = [plan.channels[int(i * len(plan.channels) / nthreads)] for i in range(nthreads)]
+
+    def one(c):
+        kw = {}
+        if c.low is not None:
+            kw["low"], kw["high"] = c.low, c.high
+        r = R.chain_run(c.mode, plan.samprate, plan.L, plan.M, plan.D, iq, carrier_hz=c.bin * plan.samprate / plan.N,
+                        lo_cycles=-c.bin / plan.N, pkt_samples=4096 if plan.L >= 4096 else 240, **kw)
+        return r.nblocks
+
+    def step():
+        with ThreadPoolExecutor(nthreads) as ex:
+            return list(ex.map(one, chans))
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    ms_per_step = dt / args.steps * 1e3
+    value = nthreads * (nb * plan.L / 1e6) / (dt / args.steps)
+    sample = (f"{nthreads} channels x {nb} blocks of {plan.name} per step, one channel per thread, FFT backend {backend}"
+              f"{'' if backend_ok else ' (auto-select failed)'}")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": plan.name, "samprate": plan.samprate, "L": plan.L, "M": plan.M, "N": plan.N,
+                   "channels_in_plan": len(plan.channels), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "realtime_channels": value / (plan.samprate / 1e6),
+    }
+    if emit:
+        print(json.dumps(line))
+    return line
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+
+def run_ours(args, plan):
+    import torch
+    import torch.distributed as dist
+    from ka9q_sdr_b200 import channelizer as ch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    multi = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if multi:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B = args.blocks
+    c = ch.Channelizer(plan.samprate, plan.L, plan.M, plan.D, device=local, max_blocks=B)
+    for spec in plan.channels:
+        c.add_channel(spec.mode, spec.bin, low=spec.low, high=spec.high)
+    c.commit()
+    K = c.nchan
+
+    # synthetic input (rank 0 ingests the stream); pinned host buffers for the end-to-end leg
+    nbytes_in = B * plan.L * 4
+    pin_in = ch.PinnedBuffer(nbytes_in, np.int16)
+    if rank == 0:
+        pin_in.array[:] = make_input(plan, B)
+    pin_pcm = ch.PinnedBuffer(B * c.pcm_stride * 2, np.int16)
+    in_ptr = C.c_void_p(pin_in.ptr)
+    pcm_ptr = C.c_void_p(pin_pcm.ptr)
+
+    if multi:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(ch.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        c.nccl_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+        c.sync()
+
+    def step_resident():
+        if not multi:
+            c.compute_resident(B)
+        else:
+            if rank == 0:
+                c.compute_fft_only(B)
+            c.nccl_broadcast_spectrum(B, 0)
+            c.compute_channels_only(B)
+
+    def step_e2e():
+        if not multi:
+            c.push(in_ptr, B)
+            c.compute(B)
+            c.fetch(B, pcm_ptr)
+            c.sync()
+        else:
+            # the stream enters the box once (rank 0); every rank returns its own PCM rows to the host
+            if rank == 0:
+                c.push(in_ptr, B)
+                c.compute_fft_only(B)
+            c.nccl_broadcast_spectrum(B, 0)
+            c.compute_channels_only(B)
+            c.fetch(B, pcm_ptr)
+            c.sync()
+
+    # make the ring resident (all ranks keep a ring; only rank 0's is meaningful in multi-GPU runs)
+    c.push(in_ptr, B)
+    c.compute(B)
+    c.sync()
+
+    # ---- device-resident leg: W warm-up steps, then exactly K timed steps
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    c.timer_start()
+    for _ in range(args.steps):
+        step_resident()
+    ms_total, classes = c.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if multi:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    ms_per_step = ms_total_max / args.steps
+    ms_blocks_per_s = world * K * (B * plan.L / 1e6) / (ms_per_step / 1e3)   # channel·MS/s over all ranks
+
+    # ---- end-to-end leg (host pinned buffers, H2D + D2H inside the timed region)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if multi:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * K * (B * plan.L / 1e6) / e2e_s
+    h2d = nbytes_in if True else 0
+    d2h = world * B * c.pcm_stride * 2
+
+    if rank != 0:
+        if multi:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the FM channel kernel), measured live with CUDA events
+    chan_bytes, stream_bytes = algorithmic_bytes(plan, B)
+    peak, peak_src = measured_peak_hbm()
+    dom = max(("fm", "am", "linear"), key=lambda k: classes[k][0])
+    dom_ms, dom_n = classes[dom]
+    roofline = None
+    if dom_n:
+        avg_ms = dom_ms / dom_n
+        ach = chan_bytes / (avg_ms / 1e3) / 1e9 if len({m.mode for m in plan.channels}) == 1 else None
+        if ach is None:
+            # mixed plans: only the dominant class's channels count for its kernel
+            from ka9q_sdr_b200 import modes, workloads
+            olen = plan.L // plan.D
+            dt = {"fm": 2, "am": 1, "linear": 0}[dom]
+            cb = sum(workloads.channel_block_bytes(dt, modes.get_mode(s.mode).channels if dt == 0 else 1, olen,
+                                                   modes.get_mode(s.mode).flat)
+                     for s in plan.channels if modes.get_mode(s.mode).demod_type == dt) * B
+            ach = cb / (avg_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(f"{dom}_kernel_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                    "avg_launch_ms": avg_ms, "launches": dom_n,
+                    "algorithmic_bytes_per_launch": chan_bytes,
+                    "share_of_step": dom_ms / ms_total if ms_total else None}
+
+    # ---- CPU baseline on this box's host cores (bounded sample), N=1 only
+    cpu = None
+    if not multi and not args.no_cpu_baseline:
+        try:
+            ra = argparse.Namespace(**vars(args))
+            ra.steps, ra.warmup = 2, 1
+            cpu = run_reference(ra, plan, emit=False).get("cpu_baseline")
+        except Exception as e:  # the GPU numbers stand on their own
+            cpu = {"error": str(e)}
+
+    launches_per_step = c.launches_per_call + (1 if multi else 0)
+    work_mb = (K * 2048 * 8 + K * 2048 * 4 + B * plan.N * 8 * 2 + B * c.pcm_stride * 2) / 1e6
+    line = {
+        "metric": METRIC, "value": ms_blocks_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": plan.name, "channels_per_gpu": K, "samprate": plan.samprate, "L": plan.L, "M": plan.M,
+                   "N": plan.N, "decimate": plan.D, "blocks_per_step": B, "block_ms": 20,
+                   "parallelism": "1 GPU" if not multi else f"channels x{world} (weak), NCCL spectrum broadcast from rank 0",
+                   "l2": f"per-step working set {work_mb:.0f} MB > 126 MB L2 (responses+state+spectra+PCM); no flush needed"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "realtime_channels": ms_blocks_per_s / (plan.samprate / 1e6),
+        "speedup_over_realtime": (B * 20.0) / ms_per_step,
+        "class_ms_per_step": {k: v[0] / args.steps for k, v in classes.items()},
+    }
+    print(json.dumps(line))
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg5")
+    ap.add_argument("--channels", type=int, default=None)
+    ap.add_argument("--blocks", type=int, default=4, help="20 ms blocks per step")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-blocks", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    plan = make_plan(args.config, args.channels)
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        run_reference(args, plan)
+        return 0
+    run_ours(args, plan)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -239,6 +239,12 @@ int ka9q_stream_sync(ka9q_stream *s);
  * the dominant (channel) kernels alone. Valid after ka9q_stream_sync. */
 int ka9q_stream_last_timing(ka9q_stream *s, float *total_ms, float *fft_ms, float *chan_ms);
 
+/* Timed region for benchmarks: CUDA events on the compute stream around the region, plus one event pair around every
+ * forward FFT and every channel-kernel launch inside it. class_ms[5]/class_launches[5] = {forward FFT, FM kernel,
+ * AM kernel, linear kernel, NCCL spectrum broadcast}. timer_stop synchronises. */
+int ka9q_stream_timer_start(ka9q_stream *s);
+int ka9q_stream_timer_stop(ka9q_stream *s, float *ms_total, float *class_ms, int *class_launches);
+
 /* Multi-GPU: channels are sharded by the caller (each rank adds only its own channels); the rank that owns the
  * I/Q input runs the forward FFT and broadcasts the spectrum. The caller supplies the broadcast as a callback
  * (NCCL in bench.py through torch.distributed, or ka9q_nccl_* below). When root < 0 every rank computes its own FFT. */

@@ -163,6 +163,25 @@ class Channelizer:
         _lib.check(self.lib.ka9q_stream_last_timing(self.h, C.byref(t), C.byref(f), C.byref(c)), "last_timing")
         return t.value, f.value, c.value
 
+    def timer_start(self):
+        _lib.check(self.lib.ka9q_stream_timer_start(self.h), "timer_start")
+
+    def timer_stop(self):
+        """Returns (region_ms, {class: (ms, launches)}) for classes fft, fm, am, linear, bcast."""
+        ms = C.c_float()
+        cms = (C.c_float * 5)()
+        cl = (C.c_int * 5)()
+        _lib.check(self.lib.ka9q_stream_timer_stop(self.h, C.byref(ms), cms, cl), "timer_stop")
+        names = ("fft", "fm", "am", "linear", "bcast")
+        return ms.value, {n: (cms[i], cl[i]) for i, n in enumerate(names)}
+
+    def nccl_init(self, id128: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(id128, 128)
+        _lib.check(self.lib.ka9q_stream_nccl_init(self.h, buf, rank, nranks), "nccl_init")
+
+    def nccl_broadcast_spectrum(self, nblocks: int, root: int = 0):
+        _lib.check(self.lib.ka9q_stream_nccl_broadcast_spectrum(self.h, nblocks, root), "nccl_broadcast_spectrum")
+
     # -- introspection (parity tests) ----------------------------------------------------------------------
     def response(self, chan: int):
         out = np.empty(2048, dtype=np.complex64)
@@ -197,6 +216,12 @@ class Channelizer:
             self.close()
         except Exception:
             pass
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.lib().ka9q_nccl_unique_id(buf), "ka9q_nccl_unique_id")
+    return buf.raw
 
 
 def fft_c2c(x: np.ndarray, sign: int = -1, device: int = 0) -> np.ndarray:

@@ -82,6 +82,42 @@ struct ka9q_stream {
   int last_nblocks = 0;
   // NCCL (dlopen'ed)
   void* nccl_comm = nullptr;
+  // live timing of the timed region (bench.py): event pairs around every forward FFT and every FM/AM/linear launch
+  bool timing = false;
+  cudaEvent_t e_t0 = nullptr, e_t1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;  // (class, (start, stop))
+  size_t ev_next = 0;
+};
+
+enum TimeClass { TC_FFT = 0, TC_FM = 1, TC_AM = 2, TC_LIN = 3, TC_BCAST = 4, TC_COUNT = 5 };
+
+static cudaEvent_t timing_event(ka9q_stream* s) {
+  if (s->ev_next == s->ev_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    s->ev_pool.push_back(e);
+  }
+  return s->ev_pool[s->ev_next++];
+}
+struct TimedRegion {
+  ka9q_stream* s;
+  cudaStream_t st;
+  cudaEvent_t e1 = nullptr;
+  TimedRegion(ka9q_stream* s_, int cls, cudaStream_t st_) : s(s_), st(st_) {
+    if (!s->timing || s->ev_used.size() >= 4096) return;
+    cudaEvent_t e0 = timing_event(s);
+    e1 = timing_event(s);
+    if (!e0 || !e1) {
+      e1 = nullptr;
+      return;
+    }
+    cudaEventRecord(e0, st);
+    s->ev_used.push_back({cls, {e0, e1}});
+  }
+  ~TimedRegion() {
+    if (e1) cudaEventRecord(e1, st);
+  }
 };
 
 // ------------------------------------------------------------------ helpers
@@ -506,9 +542,12 @@ static int issue_fft(ka9q_stream* s, int nblocks, long long first_block) {
   in.energy = s->d_energy;
   K9_CUDA(cudaMemsetAsync(s->d_energy, 0, sizeof(float) * nblocks, s->s_comp));
   K9_CUDA(cudaEventRecord(s->e_fft0, s->s_comp));
-  if (bigfft_exec(&s->fwd, in, s->d_spec, s->N, s->d_tmp0, s->d_tmp1, nblocks, -1, s->s_comp)) {
-    set_error("forward FFT launch failed");
-    return -1;
+  {
+    TimedRegion tr(s, TC_FFT, s->s_comp);
+    if (bigfft_exec(&s->fwd, in, s->d_spec, s->N, s->d_tmp0, s->d_tmp1, nblocks, -1, s->s_comp)) {
+      set_error("forward FFT launch failed");
+      return -1;
+    }
   }
   K9_CUDA(cudaEventRecord(s->e_fft1, s->s_comp));
   return 0;
@@ -523,19 +562,26 @@ static int issue_channels(ka9q_stream* s, int nblocks) {
     K9_CUDA(cudaStreamWaitEvent(s->s_am, s->e_fork, 0));
     a.work = s->d_work_am;
     a.nwork = s->n_am;
-    K9_CHECK(launch_am(a, s->s_am) == 0, "am kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    {
+      TimedRegion tr(s, TC_AM, s->s_am);
+      K9_CHECK(launch_am(a, s->s_am) == 0, "am kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     K9_CUDA(cudaEventRecord(s->e_am, s->s_am));
   }
   if (s->n_lin) {
     K9_CUDA(cudaStreamWaitEvent(s->s_lin, s->e_fork, 0));
     a.work = s->d_work_lin;
     a.nwork = s->n_lin;
-    K9_CHECK(launch_linear(a, s->s_lin) == 0, "linear kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    {
+      TimedRegion tr(s, TC_LIN, s->s_lin);
+      K9_CHECK(launch_linear(a, s->s_lin) == 0, "linear kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     K9_CUDA(cudaEventRecord(s->e_lin, s->s_lin));
   }
   if (s->n_fm) {
     a.work = s->d_work_fm;
     a.nwork = s->n_fm;
+    TimedRegion tr(s, TC_FM, s->s_comp);
     K9_CHECK(launch_fm(a, s->s_comp) == 0, "fm kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (s->n_am) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_am, 0));
@@ -566,9 +612,12 @@ static int compute_impl(ka9q_stream* s, int nblocks, bool resident, bool do_fft,
   if (do_chan || !do_fft) {
     s->comp_parity ^= 1;
     K9_CUDA(cudaEventRecord(s->e_comp_done[s->comp_parity], s->s_comp));
-    if (!resident) s->block0 += nblocks;
     s->last_nblocks = nblocks;
   }
+  if (resident)
+    s->block0 = s->pushed / s->cfg.L;  // everything pushed so far counts as consumed
+  else
+    s->block0 += nblocks;
   return 0;
 }
 
@@ -690,6 +739,51 @@ int ka9q_stream_destroy(ka9q_stream* s) {
 }
 
 
+
+// ------------------------------------------------------------------ timed region (bench.py)
+// timer_start/stop bracket a region with CUDA events on the compute stream (the stream every kernel of this library
+// is launched on or joined into); while active, every forward FFT and every channel-kernel launch is also bracketed
+// by its own event pair so the per-kernel-class device time inside the region can be reported.
+int ka9q_stream_timer_start(ka9q_stream* s) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  if (!s->e_t0) {
+    K9_CUDA(cudaEventCreate(&s->e_t0));
+    K9_CUDA(cudaEventCreate(&s->e_t1));
+  }
+  s->ev_used.clear();
+  s->ev_next = 0;
+  s->timing = true;
+  K9_CUDA(cudaEventRecord(s->e_t0, s->s_comp));
+  return 0;
+}
+// ms_total: region time. class_ms[5] / class_launches[5]: summed device time and launch count of
+// {forward FFT (all passes), FM kernel, AM kernel, linear kernel, NCCL spectrum broadcast}.
+int ka9q_stream_timer_stop(ka9q_stream* s, float* ms_total, float* class_ms, int* class_launches) {
+  K9_CHECK(s && s->committed && s->timing, "timer not started");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  K9_CUDA(cudaEventRecord(s->e_t1, s->s_comp));
+  s->timing = false;
+  if (ka9q_stream_sync(s)) return -1;
+  float ms = 0;
+  K9_CUDA(cudaEventElapsedTime(&ms, s->e_t0, s->e_t1));
+  if (ms_total) *ms_total = ms;
+  float acc[TC_COUNT] = {0, 0, 0, 0, 0};
+  int cnt[TC_COUNT] = {0, 0, 0, 0, 0};
+  for (auto& u : s->ev_used) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, u.second.first, u.second.second) == cudaSuccess) {
+      acc[u.first] += t;
+      cnt[u.first]++;
+    }
+  }
+  for (int i = 0; i < TC_COUNT; i++) {
+    if (class_ms) class_ms[i] = acc[i];
+    if (class_launches) class_launches[i] = cnt[i];
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ pinned host memory
 
 void* ka9q_host_alloc(size_t bytes) {
@@ -771,7 +865,11 @@ int ka9q_stream_nccl_broadcast_spectrum(ka9q_stream* s, int nblocks, int root) {
   K9_CUDA(cudaSetDevice(s->cfg.device));
   // float32 count: 2 floats per bin; ordered on the compute stream right after the forward FFT
   const size_t count = (size_t)2 * s->N * nblocks;
-  int r = p_ncclBroadcast(s->d_spec, s->d_spec, count, /*ncclFloat32=*/7, root, (k9_ncclComm_t)s->nccl_comm, s->s_comp);
+  int r;
+  {
+    TimedRegion tr(s, TC_BCAST, s->s_comp);
+    r = p_ncclBroadcast(s->d_spec, s->d_spec, count, /*ncclFloat32=*/7, root, (k9_ncclComm_t)s->nccl_comm, s->s_comp);
+  }
   K9_CHECK(r == 0, "ncclBroadcast: %s", p_ncclGetErrorString ? p_ncclGetErrorString(r) : "error");
   return 0;
 }
