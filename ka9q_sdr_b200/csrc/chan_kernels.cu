@@ -21,35 +21,38 @@ namespace k9 {
 // ---------------------------------------------------------------- common device helpers
 
 struct CtaShared {
-  float re[FFT2048_PLANE];
-  float im[FFT2048_PLANE];
+  float2 buf[NDEC];   // FFT exchange buffer; afterwards the olen kept samples y[0..olen)
   float aux0[1024];   // FM: audio of channel A / AM,linear: amplitude
   float aux1[1024];   // FM: audio of channel B / AM: output / linear: per-sample gain
-  float red[8];
+  float red[16];
   unsigned good[32];
-  float scal[4];
+  float scal[8];
+  ChanParams P[2];
+  ChanState S[2];
 };
 
-__device__ __forceinline__ float block_sum(float v, float* red) {
-  v = warp_sum(v);
+// three block-wide reductions in one round trip: sum(a), sum(b) [or max(b) / min(c) when MINMAX]
+template <bool MINMAX>
+__device__ __forceinline__ void block_reduce3(float& a, float& b, float& c, float* red) {
+  a = warp_sum(a);
+  b = MINMAX ? warp_max(b) : warp_sum(b);
+  c = MINMAX ? warp_min(c) : warp_sum(c);
   __syncthreads();  // protect red[] from the previous use
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    red[w] = a;
+    red[4 + w] = b;
+    red[8 + w] = c;
+  }
   __syncthreads();
-  return (red[0] + red[1]) + (red[2] + red[3]);
-}
-__device__ __forceinline__ float block_max(float v, float* red) {
-  v = warp_max(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-}
-__device__ __forceinline__ float block_min(float v, float* red) {
-  v = warp_min(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  return fminf(fminf(red[0], red[1]), fminf(red[2], red[3]));
+  a = (red[0] + red[1]) + (red[2] + red[3]);
+  if (MINMAX) {
+    b = fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]));
+    c = fminf(fminf(red[8], red[9]), fminf(red[10], red[11]));
+  } else {
+    b = (red[4] + red[5]) + (red[6] + red[7]);
+    c = (red[8] + red[9]) + (red[10] + red[11]);
+  }
 }
 
 // float -> int16 as audio.c:22-28: clip, then C truncation toward zero of 32767*x
@@ -60,16 +63,16 @@ __device__ __forceinline__ int16_t scaleclip(float x) {
 }
 
 // Step 1: v[8e+r] = Y[p], p = t + 128e + 256r, Y = H .* (rotated window of X)   [filter.c:206-227]
-// ISB (CROSS_CONJ) folds the mirror bin in as filter.c:239-249 does.
-__device__ __forceinline__ float2 load_bin(const float2* __restrict__ X, int N, long long bin, int p) {
+// ISB (CROSS_CONJ) folds the mirror bin in as filter.c:239-249 does. 32-bit index math (N < 2^31).
+__device__ __forceinline__ float2 load_bin(const float2* __restrict__ X, int N, int bin, int p) {
   const int s = (p <= NDEC / 2) ? p : p - NDEC;  // signed bin offset: DC..+Nyquist, then negative frequencies
-  long long idx = bin + s;
+  int idx = bin + s;                             // bin in [0,N), |s| <= 1024 < N
   if (idx < 0) idx += N;
   if (idx >= N) idx -= N;
   return __ldg(X + idx);
 }
 
-__device__ __forceinline__ void load_filtered(const float2* __restrict__ X, int N, long long bin,
+__device__ __forceinline__ void load_filtered(const float2* __restrict__ X, int N, int bin,
                                               const float2* __restrict__ H, bool isb, float2 (&v)[16]) {
   const int t = threadIdx.x;
 #pragma unroll
@@ -102,18 +105,14 @@ __device__ __forceinline__ float2 block_phase(long long bin, long long m, int L,
   return make_float2((float)c, (float)s);
 }
 
-// Steps 1-3 for one channel-block. On return the olen kept samples are in sh.re/sh.im[0..olen) (synchronised),
-// and *sumsq / *sumamp hold this thread's partial sums of |y|^2 and |y|.
-__device__ __forceinline__ void channel_filter(const ChanLaunch& a, CtaShared& sh, int chan, const ChanParams& P, int b,
-                                               float* sumsq, float* sumamp) {
+// After the inverse transform: apply the block phase, keep the last olen samples in sh.buf[0..olen) and return this
+// thread's partial sums of |y|^2 and |y|. Caller must have synchronised after the FFT's last shared-memory reads
+// (done here) and must synchronise before other threads' samples are read (any block_reduce3 does).
+__device__ __forceinline__ void keep_output(const ChanLaunch& a, CtaShared& sh, const float2 (&v)[16], float2 ph, int chan,
+                                            int b, float* sumsq, float* sumamp) {
   const int t = threadIdx.x;
-  const float2* X = a.spec + (long long)b * a.spec_stride;
-  float2 v[16];
-  load_filtered(X, a.N, P.bin, a.resp + (long long)chan * NDEC, (P.flags & CH_ISB) != 0, v);
-  fft2048<+1>(v, sh.re, sh.im, a.tw2048);
-  const float2 ph = block_phase(P.bin, a.block0 + b, a.L, a.M, a.N);
   const int first = NDEC - a.olen;
-  __syncthreads();  // everyone has read its stage-3 inputs; planes can be reused for y
+  __syncthreads();  // everyone has read its stage-3 inputs; the buffer can be reused for y
   float ssq = 0.f, samp = 0.f;
 #pragma unroll
   for (int j = 0; j < 16; j++) {
@@ -121,8 +120,7 @@ __device__ __forceinline__ void channel_filter(const ChanLaunch& a, CtaShared& s
     if (n >= first) {
       const int o = n - first;
       const float2 y = cmul(v[j], ph);
-      sh.re[o] = y.x;
-      sh.im[o] = y.y;
+      sh.buf[o] = y;
       const float q = y.x * y.x + y.y * y.y;
       ssq += q;
       samp += sqrtf(q);
@@ -131,7 +129,6 @@ __device__ __forceinline__ void channel_filter(const ChanLaunch& a, CtaShared& s
   }
   *sumsq = ssq;
   *sumamp = samp;
-  __syncthreads();
 }
 
 // ---------------------------------------------------------------- FM (pairs)
@@ -154,197 +151,248 @@ __device__ __forceinline__ float fm_arg(float2 y, float2 st) {
   return atan2f(im, re);
 }
 
-__global__ void __launch_bounds__(FFT2048_THREADS) fm_kernel(const ChanLaunch a) {
+// Squelch + discriminator for one channel-block whose kept samples are in sh.buf (fm.c:86-160). Writes olen audio
+// samples to aud[], updates sh.S[h] and the status row.
+__device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& sh, int h, int c, int b, float ssq,
+                                                float samp, float* __restrict__ aud) {
+  const int t = threadIdx.x;
+  const int olen = a.olen;
+  float dummy = 0.f;
+  block_reduce3<false>(ssq, samp, dummy, sh.red);
+  const float bb_power = ssq / (2 * olen);
+  const float avg_amp = samp / ((float)M_SQRT2 * olen);
+  const float fm_variance = bb_power - avg_amp * avg_amp;
+  float snr = avg_amp * avg_amp / (2 * fm_variance) - 1;
+  snr = fmaxf(0.0f, snr);
+  int below = sh.S[h].fm_below;
+  if (snr > 2) {  // fm.c:108-113
+    below = 0;
+  } else {
+    if (++below > 1000) below = 1000;
+  }
+  const bool open = below < 2;
+  float2 new_state = make_float2(0.f, 0.f);
+  float new_last = 0.f, foffset = sh.S[h].fm_foffset, pdeviation = sh.S[h].fm_pdeviation;
+  if (open) {
+    const float min_ampl = 0.55f * 0.55f * avg_amp * avg_amp;  // fm.c:121
+    const float2 old_state = sh.S[h].fm_state;
+    const float old_last = sh.S[h].fm_lastaudio;
+    // good-sample bitmap, one ballot per 32 samples
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+      const int o = t + 128 * i;
+      bool g = false;
+      if (o < olen) {
+        const float2 y = sh.buf[o];
+        g = (y.x * y.x + y.y * y.y) > min_ampl;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, g);
+      if ((t & 31) == 0) sh.good[(t >> 5) + 4 * i] = mask;
+    }
+    __syncthreads();
+    float fsum = 0.f, pos = -INFINITY, neg = INFINITY;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+      const int o = t + 128 * i;
+      if (o < olen) {
+        const bool g = (sh.good[o >> 5] >> (o & 31)) & 1u;
+        const int src = g ? o : prev_good(sh.good, o);  // sample whose discriminator value is emitted
+        float audio;
+        if (src < 0) {
+          audio = old_last;  // no good sample yet in this block: repeat the carried one (fm.c:141)
+        } else {
+          const int pg = prev_good(sh.good, src);
+          float2 st = old_state;
+          if (pg >= 0) {
+            st = sh.buf[pg];
+            st.y = -st.y;
+          }
+          audio = fm_arg(sh.buf[src], st);
+        }
+        aud[o] = audio;
+        fsum += audio;
+        if (g && o > 0) {
+          pos = fmaxf(pos, audio);
+          neg = fminf(neg, audio);
+        }
+        if (o == 0) sh.scal[0] = g ? audio : 0.f;
+        if (o == olen - 1) sh.scal[1] = audio;
+      }
+    }
+    block_reduce3<true>(fsum, pos, neg, sh.red);
+    const float init = sh.scal[0];
+    const float pdev_pos = fmaxf(pos, init);
+    const float pdev_neg = fminf(neg, init);
+    const float avg_f = fsum / olen;
+    const int lg = prev_good(sh.good, olen);
+    new_state = old_state;
+    if (lg >= 0) {
+      new_state = sh.buf[lg];
+      new_state.y = -new_state.y;
+    }
+    new_last = sh.scal[1];
+    if (below < 1) {  // frequency offset and peak deviation only while fully open (fm.c:145-154)
+      const float dsr = a.dsamprate;
+      foffset = (float)(dsr * avg_f * (0.5 * M_1_PI));
+      pdeviation = (float)(dsr * fmaxf(pdev_pos - avg_f, -(pdev_neg - avg_f)) * (0.5 * M_1_PI));
+    }
+  } else {
+    // squelch closed (fm.c:155-160)
+    for (int o = t; o < olen; o += FFT2048_THREADS) aud[o] = 0.f;
+  }
+  __syncthreads();  // all reads of sh.S[h], sh.scal and y are done
+  if (t == 0) {
+    sh.S[h].fm_below = below;
+    sh.S[h].fm_state = new_state;
+    sh.S[h].fm_lastaudio = new_last;
+    sh.S[h].fm_foffset = foffset;
+    sh.S[h].fm_pdeviation = pdeviation;
+    ChanStatus st;
+    st.bb_power = bb_power;
+    st.snr = snr;
+    st.foffset = foffset;
+    st.pdeviation = pdeviation;
+    st.agc_gain = sh.P[h].fm_gain;
+    st.squelch_open = open ? 1 : 0;
+    st.reserved[0] = st.reserved[1] = 0.f;
+    a.status[(long long)b * a.nchan_total + c] = st;
+  }
+}
+
+__global__ void __launch_bounds__(FFT2048_THREADS, 4) fm_kernel(const ChanLaunch a) {
   __shared__ CtaShared sh;
   const int t = threadIdx.x;
   const int2 wk = a.work[blockIdx.x];
-  const int chans[2] = {wk.x, wk.y};
-  ChanParams P[2];
-  ChanState S[2];
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    if (chans[h] >= 0) {
-      P[h] = a.params[chans[h]];
-      S[h] = a.state[chans[h]];
+  if (t < 2) {
+    const int c = t ? wk.y : wk.x;
+    if (c >= 0) {
+      sh.P[t] = a.params[c];
+      sh.S[t] = a.state[c];
     }
   }
+  __syncthreads();
   const int olen = a.olen;
   const int first = NDEC - olen;
-  const bool filtered = P[0].audio_slot >= 0;
+  const bool filtered = sh.P[0].audio_slot >= 0;
+  float* hist[2] = {a.audio_hist ? a.audio_hist + (long long)wk.x * NDEC : nullptr,
+                    (a.audio_hist && wk.y >= 0) ? a.audio_hist + (long long)wk.y * NDEC : nullptr};
+  float2 v[16];
 
   for (int b = 0; b < a.nblocks; b++) {
     const long long m = a.block0 + b;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      float* aud = h ? sh.aux1 : sh.aux0;
-      const int c = chans[h];
-      if (c < 0) {
-        for (int o = t; o < olen; o += FFT2048_THREADS) aud[o] = 0.f;
-        continue;
-      }
-      float ssq, samp;
-      channel_filter(a, sh, c, P[h], b, &ssq, &samp);
-      // squelch statistics (fm.c:91-103)
-      const float tot_sq = block_sum(ssq, sh.red);
-      const float tot_amp = block_sum(samp, sh.red);
-      const float bb_power = tot_sq / (2 * olen);
-      const float avg_amp = tot_amp / ((float)M_SQRT2 * olen);
-      const float fm_variance = bb_power - avg_amp * avg_amp;
-      float snr = avg_amp * avg_amp / (2 * fm_variance) - 1;
-      snr = fmaxf(0.0f, snr);
-      if (snr > 2) {
-        S[h].fm_below = 0;
-      } else {
-        if (++S[h].fm_below > 1000) S[h].fm_below = 1000;
-      }
-      const bool open = S[h].fm_below < 2;
-      if (open) {
-        const float min_ampl = 0.55f * 0.55f * avg_amp * avg_amp;  // fm.c:121
-        // good-sample bitmap, one ballot per 32 samples
-        for (int i = 0; i < 8; i++) {
-          const int o = t + 128 * i;
-          bool g = false;
-          if (o < olen) {
-            const float q = sh.re[o] * sh.re[o] + sh.im[o] * sh.im[o];
-            g = q > min_ampl;
-          }
-          const unsigned mask = __ballot_sync(0xffffffffu, g);
-          if ((t & 31) == 0) sh.good[(t >> 5) + 4 * i] = mask;
-        }
-        __syncthreads();
-        float fsum = 0.f, pos = -INFINITY, neg = INFINITY;
-        for (int i = 0; i < 8; i++) {
-          const int o = t + 128 * i;
-          if (o < olen) {
-            const bool g = (sh.good[o >> 5] >> (o & 31)) & 1u;
-            const int src = g ? o : prev_good(sh.good, o);  // sample whose discriminator value is emitted
-            float audio;
-            if (src < 0) {
-              audio = S[h].fm_lastaudio;  // no good sample yet in this block: repeat the carried one (fm.c:141)
-            } else {
-              const int pg = prev_good(sh.good, src);
-              const float2 st = (pg >= 0) ? make_float2(sh.re[pg], -sh.im[pg]) : S[h].fm_state;
-              audio = fm_arg(make_float2(sh.re[src], sh.im[src]), st);
-            }
-            aud[o] = audio;
-            fsum += audio;
-            if (g && o > 0) {
-              pos = fmaxf(pos, audio);
-              neg = fminf(neg, audio);
-            }
-            if (o == 0) sh.scal[0] = g ? audio : 0.f;
-            if (o == olen - 1) sh.scal[1] = audio;
-          }
-        }
-        const float tot_f = block_sum(fsum, sh.red);
-        const float init = sh.scal[0];
-        const float pdev_pos = fmaxf(block_max(pos, sh.red), init);
-        const float pdev_neg = fminf(block_min(neg, sh.red), init);
-        const float avg_f = tot_f / olen;
-        // carried discriminator state
-        const int lg = prev_good(sh.good, olen);
-        if (lg >= 0) S[h].fm_state = make_float2(sh.re[lg], -sh.im[lg]);
-        S[h].fm_lastaudio = sh.scal[1];
-        // frequency offset and peak deviation, only while the squelch is fully open (fm.c:145-154)
-        if (S[h].fm_below < 1) {
-          const float dsr = a.dsamprate;
-          S[h].fm_foffset = (float)(dsr * avg_f * (0.5 * M_1_PI));
-          S[h].fm_pdeviation = (float)(dsr * fmaxf(pdev_pos - avg_f, -(pdev_neg - avg_f)) * (0.5 * M_1_PI));
-        }
-      } else {
-        // squelch closed (fm.c:155-160)
-        S[h].fm_state = make_float2(0.f, 0.f);
-        S[h].fm_lastaudio = 0.f;
-        for (int o = t; o < olen; o += FFT2048_THREADS) aud[o] = 0.f;
-      }
-      if (t == 0) {
-        ChanStatus st;
-        st.bb_power = bb_power;
-        st.snr = snr;
-        st.foffset = S[h].fm_foffset;
-        st.pdeviation = S[h].fm_pdeviation;
-        st.agc_gain = P[h].fm_gain;
-        st.squelch_open = open ? 1 : 0;
-        st.reserved[0] = st.reserved[1] = 0.f;
-        a.status[(long long)b * a.nchan_total + c] = st;
-      }
-      __syncthreads();
-    }
-    // ---- post-detection audio filter for the pair: REAL overlap-save, L=olen, M=NDEC-olen+1 (fm.c:39-66,162-171).
-    // Two real channels ride one complex transform: z = audA + j audB, filtered by the real impulse response.
+    const float2* X = a.spec + (long long)b * a.spec_stride;
     int16_t* pcm_row = a.pcm + (long long)b * a.pcm_stride;
-    if (filtered) {
-      float2 v[16];
-      const int ringbase = (int)(((m + 1) * (long long)olen) & (NDEC - 1));
-      float* hA = a.audio_hist + (long long)chans[0] * NDEC;
-      float* hB = chans[1] >= 0 ? a.audio_hist + (long long)chans[1] * NDEC : nullptr;
+    // Four transforms per pair-block share ONE copy of the FFT code: job 0/1 = predetection filter of channel A/B,
+    // job 2 = forward transform of the audio pair (as conj(IFFT(conj z))), job 3 = its inverse.
+#pragma unroll 1
+    for (int job = 0; job < 4; job++) {
+      const int h = job & 1;
+      const int c = h ? wk.y : wk.x;
+      if (job < 2) {
+        if (c < 0) {
+          for (int o = t; o < olen; o += FFT2048_THREADS) sh.aux1[o] = 0.f;
+          continue;
+        }
+        if (t == 0) {
+          const float2 ph = block_phase(sh.P[h].bin, m, a.L, a.M, a.N);
+          sh.scal[2] = ph.x;
+          sh.scal[3] = ph.y;
+        }
+        load_filtered(X, a.N, (int)sh.P[h].bin, a.resp + (long long)c * NDEC, false, v);
+      } else if (job == 2) {
+        if (!filtered) break;
+        // REAL overlap-save input of the post-detection filter, L=olen, M=NDEC-olen+1 (fm.c:39-43): two real channels
+        // ride one complex transform, z = audA + j audB (the filter's impulse response is real). History lives in a
+        // 2048-sample ring per channel; this block's new samples are appended to it here.
+        const int ringbase = (int)(((m + 1) * (long long)olen) & (NDEC - 1));
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
+        for (int e = 0; e < 2; e++) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-          const int p = t + 128 * e + 256 * r;
-          float2 z;
-          if (p < first) {
+          for (int r = 0; r < 8; r++) {
+            const int p = t + 128 * e + 256 * r;
             const int ri = (ringbase + p) & (NDEC - 1);
-            z.x = hA[ri];
-            z.y = hB ? hB[ri] : 0.f;
-          } else {
-            z.x = sh.aux0[p - first];
-            z.y = sh.aux1[p - first];
-            // the new samples become history for the next blocks
-            const int ri = (ringbase + p) & (NDEC - 1);
-            hA[ri] = z.x;
-            if (hB) hB[ri] = z.y;
+            float2 z;
+            if (p < first) {
+              z.x = hist[0][ri];
+              z.y = hist[1] ? hist[1][ri] : 0.f;
+            } else {
+              z.x = sh.aux0[p - first];
+              z.y = sh.aux1[p - first];
+              hist[0][ri] = z.x;
+              if (hist[1]) hist[1][ri] = z.y;
+            }
+            v[8 * e + r] = make_float2(z.x, -z.y);  // conj: forward transform through the backward code
           }
-          v[8 * e + r] = z;
         }
       }
-      fft2048<-1>(v, sh.re, sh.im, a.tw2048);
-      const float2* R = a.audio_resp + (long long)P[0].audio_slot * NDEC;
+      fft2048<+1>(v, sh.buf, a.tw2048);
+      if (job < 2) {
+        float ssq, samp;
+        keep_output(a, sh, v, make_float2(sh.scal[2], sh.scal[3]), c, b, &ssq, &samp);
+        fm_discriminate(a, sh, h, c, b, ssq, samp, h ? sh.aux1 : sh.aux0);
+      } else if (job == 2) {
+        const float2* R = a.audio_resp + (long long)sh.P[0].audio_slot * NDEC;
 #pragma unroll
-      for (int j = 0; j < 16; j++) v[j] = cmul(v[j], __ldg(R + t + 128 * j));
-      fft2048_out_to_in(v);
-      fft2048<+1>(v, sh.re, sh.im, a.tw2048);
+        for (int j = 0; j < 16; j++) {
+          const float2 Z = make_float2(v[j].x, -v[j].y);  // undo the conj: Z = FFT-(z)
+          v[j] = cmul(Z, __ldg(R + t + 128 * j));
+        }
+        fft2048_out_to_in(v);
+      } else {
+        const float gA = sh.P[0].fm_gain, gB = sh.P[1].fm_gain;
+        const int offA = sh.P[0].pcm_off, offB = sh.P[1].pcm_off;
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const int n = t + 128 * j;
-        if (n >= first) {
-          const int o = n - first;
-          pcm_row[P[0].pcm_off + o] = scaleclip(v[j].x * P[0].fm_gain);  // fm.c:169-170
-          if (chans[1] >= 0) pcm_row[P[1].pcm_off + o] = scaleclip(v[j].y * P[1].fm_gain);
+        for (int j = 0; j < 16; j++) {
+          const int n = t + 128 * j;
+          if (n >= first) {
+            const int o = n - first;
+            pcm_row[offA + o] = scaleclip(v[j].x * gA);  // fm.c:169-170
+            if (wk.y >= 0) pcm_row[offB + o] = scaleclip(v[j].y * gB);
+          }
         }
       }
-    } else {
+    }
+    if (!filtered) {
       // FLAT: raw discriminator output goes out unfiltered and unscaled (fm.c:55,164-172)
+      __syncthreads();
       for (int o = t; o < olen; o += FFT2048_THREADS) {
-        pcm_row[P[0].pcm_off + o] = scaleclip(sh.aux0[o]);
-        if (chans[1] >= 0) pcm_row[P[1].pcm_off + o] = scaleclip(sh.aux1[o]);
+        pcm_row[sh.P[0].pcm_off + o] = scaleclip(sh.aux0[o]);
+        if (wk.y >= 0) pcm_row[sh.P[1].pcm_off + o] = scaleclip(sh.aux1[o]);
       }
     }
     __syncthreads();
   }
-  if (t == 0) {
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-      if (chans[h] >= 0) a.state[chans[h]] = S[h];
+  if (t < 2) {
+    const int c = t ? wk.y : wk.x;
+    if (c >= 0) a.state[c] = sh.S[t];
   }
 }
 
 // ---------------------------------------------------------------- AM (envelope)
 
-__global__ void __launch_bounds__(FFT2048_THREADS) am_kernel(const ChanLaunch a) {
+__global__ void __launch_bounds__(FFT2048_THREADS, 4) am_kernel(const ChanLaunch a) {
   __shared__ CtaShared sh;
   const int t = threadIdx.x;
   const int c = a.work[blockIdx.x].x;
   const ChanParams P = a.params[c];
   ChanState S = a.state[c];
   const int olen = a.olen;
+  float2 v[16];
+#pragma unroll 1
   for (int b = 0; b < a.nblocks; b++) {
     float ssq, samp;
-    channel_filter(a, sh, c, P, b, &ssq, &samp);
-    for (int o = t; o < olen; o += FFT2048_THREADS)
-      sh.aux0[o] = sqrtf(sh.re[o] * sh.re[o] + sh.im[o] * sh.im[o]);  // am.c:56-58
-    const float signal = block_sum(ssq, sh.red);                      // includes the barrier publishing aux0
+    load_filtered(a.spec + (long long)b * a.spec_stride, a.N, (int)P.bin, a.resp + (long long)c * NDEC, false, v);
+    fft2048<+1>(v, sh.buf, a.tw2048);
+    // envelope detection ignores the block's LO phase, but the captured filter output must carry it
+    keep_output(a, sh, v, block_phase(P.bin, a.block0 + b, a.L, a.M, a.N), c, b, &ssq, &samp);
+    __syncthreads();
+    for (int o = t; o < olen; o += FFT2048_THREADS) {
+      const float2 y = sh.buf[o];
+      sh.aux0[o] = sqrtf(y.x * y.x + y.y * y.y);  // am.c:56-58
+    }
+    float d0 = 0.f, d1 = 0.f;
+    block_reduce3<false>(ssq, d0, d1, sh.red);  // includes the barrier publishing aux0
+    const float signal = ssq;
     if (t == 0) {
       // strictly serial recurrences: carrier-DC tracker and hang AGC (am.c:60-74); one lane, original operation order
       float gain = S.agc_gain, dc = S.am_dc;
@@ -395,25 +443,32 @@ __global__ void __launch_bounds__(FFT2048_THREADS) am_kernel(const ChanLaunch a)
 
 // ---------------------------------------------------------------- linear (SSB / CW / IQ / ISB), no PLL
 
-__global__ void __launch_bounds__(FFT2048_THREADS) linear_kernel(const ChanLaunch a) {
+__global__ void __launch_bounds__(FFT2048_THREADS, 4) linear_kernel(const ChanLaunch a) {
   __shared__ CtaShared sh;
   const int t = threadIdx.x;
   const int c = a.work[blockIdx.x].x;
   const ChanParams P = a.params[c];
   ChanState S = a.state[c];
   const int olen = a.olen;
+  float2 v[16];
+#pragma unroll 1
   for (int b = 0; b < a.nblocks; b++) {
     float ssq, samp;
-    channel_filter(a, sh, c, P, b, &ssq, &samp);
-    float sig = 0.f, noi = 0.f;
+    load_filtered(a.spec + (long long)b * a.spec_stride, a.N, (int)P.bin, a.resp + (long long)c * NDEC,
+                  (P.flags & CH_ISB) != 0, v);
+    fft2048<+1>(v, sh.buf, a.tw2048);
+    keep_output(a, sh, v, block_phase(P.bin, a.block0 + b, a.L, a.M, a.N), c, b, &ssq, &samp);
+    __syncthreads();
+    float sig = 0.f, noi = 0.f, d2 = 0.f;
     for (int o = t; o < olen; o += FFT2048_THREADS) {
-      const float rp = sh.re[o] * sh.re[o], ip = sh.im[o] * sh.im[o];  // linear.c:256-259
+      const float2 y = sh.buf[o];
+      const float rp = y.x * y.x, ip = y.y * y.y;  // linear.c:256-259
       sig += rp;
       noi += ip;
       sh.aux0[o] = sqrtf(rp + ip);
     }
-    const float signal = block_sum(sig, sh.red);
-    const float noise = block_sum(noi, sh.red);
+    block_reduce3<false>(sig, noi, d2, sh.red);
+    const float signal = sig, noise = noi;
     if (t == 0) {
       // hang AGC (linear.c:269-280): serial, one lane, original operation order
       float gain = S.agc_gain;
@@ -444,7 +499,8 @@ __global__ void __launch_bounds__(FFT2048_THREADS) linear_kernel(const ChanLaunc
     const bool shifted = P.shift_cycles != 0.0;
     for (int o = t; o < olen; o += FFT2048_THREADS) {
       const float g = sh.aux1[o];
-      float2 z = make_float2(sh.re[o] * g, sh.im[o] * g);  // linear.c:280
+      const float2 y = sh.buf[o];
+      float2 z = make_float2(y.x * g, y.y * g);  // linear.c:280
       if (shifted) {
         // post-detection shift oscillator (linear.c:283-289, osc.c:39-51): phasor(n) = exp(j*2*pi*f*n), n counted
         // from the first sample the oscillator was stepped on

@@ -10,20 +10,23 @@
 // so the output of one call is, up to the register permutation j = e + 2r, exactly the input layout of the next —
 // forward FFT -> pointwise multiply -> inverse FFT needs no exchange in between.
 //
-// Shared memory: two float planes (re, im) of FFT2048_PLANE floats, padded so every exchange is bank-conflict free:
-//   exchange 1 index a -> a + (a >> 5);  exchange 2 index a -> a + 8*(a >> 7).
+// Shared memory: one float2[2048] buffer, no padding. Both exchanges are bank-conflict free for 64-bit accesses
+// (16 lanes per wavefront) through XOR swizzles of the low index bits:
+//   exchange 1: a -> a ^ ((a >> 3) & 15)      exchange 2: a -> a ^ (((a >> 7) & 1) << 3)
+//
+// The body is deliberately instantiated ONCE per kernel (callers loop over their transforms and use
+// conj(FFT(conj x)) for the opposite sign): the unrolled butterflies are ~25 KB of SASS and several copies thrash the
+// instruction cache (measured: stall_no_instruction was the top stall with four inlined copies).
 #pragma once
 #include "fft_regs.cuh"
 
 namespace k9 {
 
 constexpr int FFT2048_THREADS = 128;
-constexpr int FFT2048_PLANE = 2176;  // >= 2047 + 8*15 + 1
 
 // tw: W_2048^a = exp(-2*pi*i*a/2048), a in [0,2048) (forward sign; conjugated here when SIGN=+1)
 template <int SIGN>
-__device__ __forceinline__ void fft2048(float2 (&v)[16], float* __restrict__ sre, float* __restrict__ sim,
-                                        const float2* __restrict__ tw) {
+__device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb, const float2* __restrict__ tw) {
   const int t = threadIdx.x;
   // ---- stage 1: two radix-8 butterflies, p = t + 128e; y1[8p + j] = w_2048^(p j) * DFT8 ----
 #pragma unroll
@@ -37,54 +40,46 @@ __device__ __forceinline__ void fft2048(float2 (&v)[16], float* __restrict__ sre
       v[8 * e + j] = cmul(v[8 * e + j], w);
     }
   }
-  __syncthreads();  // WAR: previous users of the planes are done
+  __syncthreads();  // WAR: previous users of the buffer are done
+  {
+    const int sw = t & 15;
 #pragma unroll
-  for (int e = 0; e < 2; e++) {
-    const int p = t + 128 * e;
+    for (int e = 0; e < 2; e++) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int a = 8 * p + j;
-      const int ap = a + (a >> 5);
-      sre[ap] = v[8 * e + j].x;
-      sim[ap] = v[8 * e + j].y;
+      for (int j = 0; j < 8; j++) {
+        const int a = 8 * (t + 128 * e) + j;
+        sb[a ^ sw] = v[8 * e + j];
+      }
     }
   }
   __syncthreads();
   // ---- stage 2: radix 16 on n=256, s=8: thread t = q + 8p'; reads y1[t + 128 r] ----
+  {
+    const int sw = t >> 3;
 #pragma unroll
-  for (int r = 0; r < 16; r++) {
-    const int a = t + 128 * r;
-    const int ap = a + (a >> 5);
-    v[r] = make_float2(sre[ap], sim[ap]);
+    for (int r = 0; r < 16; r++) v[r] = sb[(t + 128 * r) ^ sw];
   }
   Dft<16, SIGN>::run(v);
   {
     const int pp = t >> 3;  // p'
 #pragma unroll
     for (int j = 1; j < 16; j++) {
-      float2 w = __ldg(tw + ((8 * pp * j) & 2047));
+      float2 w = __ldg(tw + 8 * pp * j);
       if (SIGN > 0) w.y = -w.y;
       v[j] = cmul(v[j], w);
     }
   }
-  __syncthreads();  // WAR on the planes
+  __syncthreads();  // WAR on the buffer
   {
     const int q = t & 7, pp = t >> 3;
+    const int base = (q + 128 * pp) ^ ((pp & 1) << 3);
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const int a = q + 128 * pp + 8 * j;  // q + 8*(16 p' + j)
-      const int ap = a + 8 * (a >> 7);
-      sre[ap] = v[j].x;
-      sim[ap] = v[j].y;
-    }
+    for (int j = 0; j < 16; j++) sb[base ^ (8 * j)] = v[j];  // a = q + 128 p' + 8 j (no carries), swizzled
   }
   __syncthreads();
   // ---- stage 3: radix 16 on n=16, s=128: thread t reads y2[t + 128 r], writes X[t + 128 j] ----
 #pragma unroll
-  for (int r = 0; r < 16; r++) {
-    const int ap = t + 136 * r;  // a = t + 128 r; a + 8*(a>>7) = t + 136 r
-    v[r] = make_float2(sre[ap], sim[ap]);
-  }
+  for (int r = 0; r < 16; r++) v[r] = sb[(t + 128 * r) ^ ((r & 1) << 3)];
   Dft<16, SIGN>::run(v);
 }
 
