@@ -126,6 +126,9 @@ void renorm_osc(struct osc *osc);
 int is_phasor_init(const complex double x);
 #endif
 
+/* set_osc(f, r) on a fresh oscillator, then n step_osc() results as interleaved (re, im) doubles (tests, diagnostics) */
+int ka9q_osc_run(double f, double r, long n, double *out);
+
 /* reference decimate.h:4-11 */
 struct hb15_state {
   float coeffs[4];

@@ -61,7 +61,7 @@ EXPORTED = [
     "ka9q_nccl_unique_id", "ka9q_stream_nccl_init", "ka9q_stream_nccl_broadcast_spectrum", "ka9q_stream_get_response",
     "ka9q_stream_get_filter_output", "ka9q_stream_get_spectrum", "ka9q_stream_get_if_energy", "ka9q_fft_c2c",
     "ka9q_fft_plan_describe", "ka9q_hb15_cascade", "ka9q_host_alloc", "ka9q_host_free", "ka9q_stream_timer_start",
-    "ka9q_stream_timer_stop",
+    "ka9q_stream_timer_stop", "ka9q_osc_run",
 ]
 
 
@@ -111,6 +111,7 @@ def lib():
     L.ka9q_hb15_cascade.argtypes = [ci, ci, vp, vp, ci, vp]
     L.ka9q_stream_timer_start.argtypes = [vp]
     L.ka9q_stream_timer_stop.argtypes = [vp, C.POINTER(cf), C.POINTER(cf), C.POINTER(ci)]
+    L.ka9q_osc_run.argtypes = [C.c_double, C.c_double, C.c_long, vp]
     L.ka9q_host_alloc.argtypes = [C.c_size_t]
     L.ka9q_host_alloc.restype = vp
     L.ka9q_host_free.argtypes = [vp]

@@ -27,7 +27,7 @@ struct ChanParams {
   int hangmax;           // hangtime / samptime (am.c:29, linear.c:37)
   double shift_cycles;   // post-detection shift, cycles per output sample (radio.c:313)
   int audio_slot;        // FM: index of the audio (de-emphasis) response, -1 = flat
-  int pad_;
+  int phase_step;        // (bin * L) mod N: per-block advance of the LO phase index
 };
 
 struct ChanState {
@@ -62,6 +62,9 @@ struct ChanLaunch {
   float dsamprate;           // decimated (output) sample rate, (float)samprate / decimate (fm.c:27)
   int nblocks;
   long long block0;          // index of the first block of this launch since stream start
+  int start0;                // (block0*L - (M-1)) mod N: stream index of the first window sample, mod N
+  const float2* twN_lo;      // forward-FFT twiddle tables: W_N^a = lo[a & 1023] * hi[a >> 10]
+  const float2* twN_hi;
   const float2* tw2048;      // W_2048 table
   // per-channel arrays
   const ChanParams* params;

@@ -1,8 +1,8 @@
-// K3: fused per-channel kernels (sm_100a, fp32, no tensor cores — this is streaming FFT/demod work, HBM/issue bound).
+// K3: fused per-channel kernels (sm_100a, fp32, no tensor cores — this is streaming FFT/demod work, issue/HBM bound).
 //
 // Each CTA (128 threads) owns one work item (an FM channel pair, or one AM / linear channel) for all blocks of the
 // launch, so the carried per-channel state (discriminator state, AGC gain/hang, DC estimate, oscillator phase)
-// lives in registers between consecutive 20 ms blocks and touches HBM once per launch.
+// stays on chip between consecutive 20 ms blocks and touches HBM once per launch.
 //
 // Per block and channel (reference file:line in brackets):
 //   1. bin rotation: read the 2048-bin window of the shared N-point spectrum centred on the channel's carrier bin
@@ -27,11 +27,12 @@ struct CtaShared {
   float red[16];
   unsigned good[32];
   float scal[8];
+  int ephase[2];      // (k * block_start) mod N per channel of the work item
   ChanParams P[2];
   ChanState S[2];
 };
 
-// three block-wide reductions in one round trip: sum(a), sum(b) [or max(b) / min(c) when MINMAX]
+// three block-wide reductions in one round trip: sum(a), sum(b), sum(c) — or sum(a), max(b), min(c) when MINMAX
 template <bool MINMAX>
 __device__ __forceinline__ void block_reduce3(float& a, float& b, float& c, float* red) {
   a = warp_sum(a);
@@ -57,9 +58,10 @@ __device__ __forceinline__ void block_reduce3(float& a, float& b, float& c, floa
 
 // float -> int16 as audio.c:22-28: clip, then C truncation toward zero of 32767*x
 __device__ __forceinline__ int16_t scaleclip(float x) {
-  if (x >= 1.0f) return 32767;
-  if (x <= -1.0f) return -32768;
-  return (int16_t)(int)(32767.0f * x);
+  int v = __float2int_rz(32767.0f * x);  // (short)(SHRT_MAX * x): truncation toward zero
+  v = (x <= -1.0f) ? -32768 : v;
+  v = (x >= 1.0f) ? 32767 : v;
+  return (int16_t)v;
 }
 
 // Step 1: v[8e+r] = Y[p], p = t + 128e + 256r, Y = H .* (rotated window of X)   [filter.c:206-227]
@@ -72,63 +74,80 @@ __device__ __forceinline__ float2 load_bin(const float2* __restrict__ X, int N, 
   return __ldg(X + idx);
 }
 
-__device__ __forceinline__ void load_filtered(const float2* __restrict__ X, int N, int bin,
-                                              const float2* __restrict__ H, bool isb, float2 (&v)[16]) {
+// Rolled (code-size matters more than unrolling here: the unrolled variant pushed the kernel past the instruction
+// cache and made instruction fetch the top stall): stage Y into the shared buffer in natural order, p = t + 128k.
+template <bool ISB>
+__device__ __forceinline__ void stage_filtered(const float2* __restrict__ X, int N, int bin,
+                                               const float2* __restrict__ H, float2* __restrict__ buf) {
   const int t = threadIdx.x;
-#pragma unroll
-  for (int e = 0; e < 2; e++) {
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int p = t + 128 * e + 256 * r;
-      float2 y = cmul(__ldg(H + p), load_bin(X, N, bin, p));
-      if (isb && p != 0 && p != NDEC / 2) {
-        const int pm = NDEC - p;
-        float2 ym = cmul(__ldg(H + pm), load_bin(X, N, bin, pm));
-        if (p < NDEC / 2)
-          y = make_float2(y.x + ym.x, y.y - ym.y);  // pos + conj(neg)
-        else
-          y = make_float2(y.x - ym.x, y.y + ym.y);  // neg - conj(pos)
-      }
-      v[8 * e + r] = y;
+#pragma unroll 4
+  for (int k = 0; k < 16; k++) {
+    const int p = t + 128 * k;
+    float2 y = cmul(__ldg(H + p), load_bin(X, N, bin, p));
+    if (ISB && p != 0 && p != NDEC / 2) {
+      const int pm = NDEC - p;
+      const float2 ym = cmul(__ldg(H + pm), load_bin(X, N, bin, pm));
+      if (p < NDEC / 2)
+        y = make_float2(y.x + ym.x, y.y - ym.y);  // pos + conj(neg)
+      else
+        y = make_float2(y.x - ym.x, y.y + ym.y);  // neg - conj(pos)
     }
+    buf[p] = y;
   }
 }
 
-// exp(j*theta_m) for block m of a channel at bin k (Appendix C): theta = 2*pi*((-k*(m*L-(M-1))) mod N)/N
-__device__ __forceinline__ float2 block_phase(long long bin, long long m, int L, int M, int N) {
-  long long start = (m * (long long)L - (long long)(M - 1)) % N;  // may be negative
-  if (start < 0) start += N;
-  long long e = (bin % N) * start % N;  // bin in [0,N), start in [0,N): product < 2^62
-  e = (N - e) % N;                      // -k*start mod N
-  double s, c;
-  sincospi(2.0 * (double)e / (double)N, &s, &c);
-  return make_float2((float)c, (float)s);
+// registers <- staged input: v[8e + r] = buf[t + 128e + 256r] (conflict-free, consecutive lanes)
+__device__ __forceinline__ void load16(float2 (&v)[16], const float2* __restrict__ buf) {
+  const float2* bp = buf + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 2; e++)
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[8 * e + r] = bp[128 * e + 256 * r];
+}
+// transform output -> buffer in natural order: buf[t + 128j] = v[j], only the rows that hold kept samples (j >= jb)
+__device__ __forceinline__ void store16(const float2 (&v)[16], float2* __restrict__ buf, int jb) {
+  float2* bp = buf + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 16; j++)
+    if (j >= jb) bp[128 * j] = v[j];
 }
 
-// After the inverse transform: apply the block phase, keep the last olen samples in sh.buf[0..olen) and return this
-// thread's partial sums of |y|^2 and |y|. Caller must have synchronised after the FFT's last shared-memory reads
-// (done here) and must synchronise before other threads' samples are read (any block_reduce3 does).
-__device__ __forceinline__ void keep_output(const ChanLaunch& a, CtaShared& sh, const float2 (&v)[16], float2 ph, int chan,
-                                            int b, float* sumsq, float* sumamp) {
-  const int t = threadIdx.x;
-  const int first = NDEC - a.olen;
-  __syncthreads();  // everyone has read its stage-3 inputs; the buffer can be reused for y
+// Per-block LO phase (Appendix C): exp(j*2*pi*((-k*start_m) mod N)/N) = W_N^(e), e = (k*start_m) mod N with the forward
+// table W_N^a = exp(-2*pi*i*a/N) split as lo[a & 1023] * hi[a >> 10] (the forward FFT's own twiddle tables).
+__device__ __forceinline__ float2 phase_from_index(const ChanLaunch& a, int e) {
+  return cmul(__ldg(a.twN_lo + (e & 1023)), __ldg(a.twN_hi + (e >> 10)));
+}
+// e for the first block of the launch: one 64-bit modular product per channel per launch
+__device__ __forceinline__ int phase_index0(long long bin, int start0, int N) { return (int)((bin * (long long)start0) % N); }
+__device__ __forceinline__ int phase_advance(int e, int step, int N) {
+  e += step;
+  return e >= N ? e - N : e;
+}
+
+// After the inverse transform (output already in buf, natural order): apply the block phase in place to the kept
+// samples n in [first, NDEC) and return this thread's partial sums of |y|^2 and |y|. Each thread touches only the
+// elements it stored itself (n = t + 128j), so no barrier is needed between store16 and this.
+__device__ __forceinline__ void phase_and_stats(float2* __restrict__ buf, int first, float2 ph, float* sumsq, float* sumamp) {
   float ssq = 0.f, samp = 0.f;
-#pragma unroll
-  for (int j = 0; j < 16; j++) {
-    const int n = t + 128 * j;
+#pragma unroll 2
+  for (int n = threadIdx.x + 128 * (first >> 7); n < NDEC; n += 128) {
     if (n >= first) {
-      const int o = n - first;
-      const float2 y = cmul(v[j], ph);
-      sh.buf[o] = y;
+      const float2 y = cmul(buf[n], ph);
+      buf[n] = y;
       const float q = y.x * y.x + y.y * y.y;
       ssq += q;
-      samp += sqrtf(q);
-      if (a.filt_dbg) a.filt_dbg[((long long)b * a.nchan_total + chan) * a.olen + o] = y;
+      // |y| for the squelch statistics only (fm.c:95): MUFU.RSQ based, ~1 ulp; it only feeds threshold decisions
+      samp += (q > 0.f) ? q * rsqrtf(q) : 0.f;
     }
   }
   *sumsq = ssq;
   *sumamp = samp;
+}
+
+// optional raw filter-output capture for the parity tests (off the hot path)
+__device__ __noinline__ void dump_filter_output(float2* dst, const float2* src, int olen) {
+#pragma unroll 1
+  for (int o = threadIdx.x; o < olen; o += FFT2048_THREADS) dst[o] = src[o];
 }
 
 // ---------------------------------------------------------------- FM (pairs)
@@ -144,7 +163,7 @@ __device__ __forceinline__ int prev_good(const unsigned* good, int o) {
   }
 }
 
-__device__ __forceinline__ float fm_arg(float2 y, float2 st) {
+__device__ __noinline__ float fm_arg(float2 y, float2 st) {
   // cargf(samp * state) (fm.c:131)
   const float re = y.x * st.x - y.y * st.y;
   const float im = y.x * st.y + y.y * st.x;
@@ -157,8 +176,10 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
                                                 float samp, float* __restrict__ aud) {
   const int t = threadIdx.x;
   const int olen = a.olen;
+  const float2* ybuf = sh.buf + (NDEC - olen);  // kept samples y[0..olen)
   float dummy = 0.f;
   block_reduce3<false>(ssq, samp, dummy, sh.red);
+  if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen);
   const float bb_power = ssq / (2 * olen);
   const float avg_amp = samp / ((float)M_SQRT2 * olen);
   const float fm_variance = bb_power - avg_amp * avg_amp;
@@ -177,46 +198,73 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
     const float min_ampl = 0.55f * 0.55f * avg_amp * avg_amp;  // fm.c:121
     const float2 old_state = sh.S[h].fm_state;
     const float old_last = sh.S[h].fm_lastaudio;
-    // good-sample bitmap, one ballot per 32 samples
-#pragma unroll 1
+    // good-sample flags: one ballot per 32 samples; all_good short-cuts the common case of a clean block
+    bool mine_good = true;
+#pragma unroll 2
     for (int i = 0; i < 8; i++) {
       const int o = t + 128 * i;
       bool g = false;
       if (o < olen) {
-        const float2 y = sh.buf[o];
+        const float2 y = ybuf[o];
         g = (y.x * y.x + y.y * y.y) > min_ampl;
+        mine_good = mine_good && g;
       }
       const unsigned mask = __ballot_sync(0xffffffffu, g);
       if ((t & 31) == 0) sh.good[(t >> 5) + 4 * i] = mask;
     }
-    __syncthreads();
+    const bool all_good = __syncthreads_and(mine_good);  // also publishes sh.good
     float fsum = 0.f, pos = -INFINITY, neg = INFINITY;
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-      const int o = t + 128 * i;
-      if (o < olen) {
-        const bool g = (sh.good[o >> 5] >> (o & 31)) & 1u;
-        const int src = g ? o : prev_good(sh.good, o);  // sample whose discriminator value is emitted
-        float audio;
-        if (src < 0) {
-          audio = old_last;  // no good sample yet in this block: repeat the carried one (fm.c:141)
-        } else {
-          const int pg = prev_good(sh.good, src);
+    if (all_good) {
+      // every sample passes the blanking threshold: audio[n] = arg(y[n] * conj(y[n-1])) (fm.c:130-132)
+#pragma unroll 2
+      for (int i = 0; i < 8; i++) {
+        const int o = t + 128 * i;
+        if (o < olen) {
           float2 st = old_state;
-          if (pg >= 0) {
-            st = sh.buf[pg];
+          if (o > 0) {
+            st = ybuf[o - 1];
             st.y = -st.y;
           }
-          audio = fm_arg(sh.buf[src], st);
+          const float audio = fm_arg(ybuf[o], st);
+          aud[o] = audio;
+          fsum += audio;
+          if (o > 0) {
+            pos = fmaxf(pos, audio);
+            neg = fminf(neg, audio);
+          } else {
+            sh.scal[0] = audio;
+          }
+          if (o == olen - 1) sh.scal[1] = audio;
         }
-        aud[o] = audio;
-        fsum += audio;
-        if (g && o > 0) {
-          pos = fmaxf(pos, audio);
-          neg = fminf(neg, audio);
+      }
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < 8; i++) {
+        const int o = t + 128 * i;
+        if (o < olen) {
+          const bool g = (sh.good[o >> 5] >> (o & 31)) & 1u;
+          const int src = g ? o : prev_good(sh.good, o);  // sample whose discriminator value is emitted
+          float audio;
+          if (src < 0) {
+            audio = old_last;  // no good sample yet in this block: repeat the carried one (fm.c:141)
+          } else {
+            const int pg = prev_good(sh.good, src);
+            float2 st = old_state;
+            if (pg >= 0) {
+              st = ybuf[pg];
+              st.y = -st.y;
+            }
+            audio = fm_arg(ybuf[src], st);
+          }
+          aud[o] = audio;
+          fsum += audio;
+          if (g && o > 0) {
+            pos = fmaxf(pos, audio);
+            neg = fminf(neg, audio);
+          }
+          if (o == 0) sh.scal[0] = g ? audio : 0.f;
+          if (o == olen - 1) sh.scal[1] = audio;
         }
-        if (o == 0) sh.scal[0] = g ? audio : 0.f;
-        if (o == olen - 1) sh.scal[1] = audio;
       }
     }
     block_reduce3<true>(fsum, pos, neg, sh.red);
@@ -224,10 +272,10 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
     const float pdev_pos = fmaxf(pos, init);
     const float pdev_neg = fminf(neg, init);
     const float avg_f = fsum / olen;
-    const int lg = prev_good(sh.good, olen);
+    const int lg = all_good ? olen - 1 : prev_good(sh.good, olen);
     new_state = old_state;
     if (lg >= 0) {
-      new_state = sh.buf[lg];
+      new_state = ybuf[lg];
       new_state.y = -new_state.y;
     }
     new_last = sh.scal[1];
@@ -238,6 +286,7 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
     }
   } else {
     // squelch closed (fm.c:155-160)
+#pragma unroll 1
     for (int o = t; o < olen; o += FFT2048_THREADS) aud[o] = 0.f;
   }
   __syncthreads();  // all reads of sh.S[h], sh.scal and y are done
@@ -259,7 +308,7 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
   }
 }
 
-__global__ void __launch_bounds__(FFT2048_THREADS, 4) fm_kernel(const ChanLaunch a) {
+__global__ void __launch_bounds__(FFT2048_THREADS, 5) fm_kernel(const ChanLaunch a) {
   __shared__ CtaShared sh;
   const int t = threadIdx.x;
   const int2 wk = a.work[blockIdx.x];
@@ -268,11 +317,13 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) fm_kernel(const ChanLaunch
     if (c >= 0) {
       sh.P[t] = a.params[c];
       sh.S[t] = a.state[c];
+      sh.ephase[t] = phase_index0(sh.P[t].bin, a.start0, a.N);
     }
   }
   __syncthreads();
   const int olen = a.olen;
   const int first = NDEC - olen;
+  const int jb = first >> 7, rem = first & 127;
   const bool filtered = sh.P[0].audio_slot >= 0;
   float* hist[2] = {a.audio_hist ? a.audio_hist + (long long)wk.x * NDEC : nullptr,
                     (a.audio_hist && wk.y >= 0) ? a.audio_hist + (long long)wk.y * NDEC : nullptr};
@@ -290,64 +341,68 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) fm_kernel(const ChanLaunch
       const int c = h ? wk.y : wk.x;
       if (job < 2) {
         if (c < 0) {
+#pragma unroll 1
           for (int o = t; o < olen; o += FFT2048_THREADS) sh.aux1[o] = 0.f;
           continue;
         }
-        if (t == 0) {
-          const float2 ph = block_phase(sh.P[h].bin, m, a.L, a.M, a.N);
-          sh.scal[2] = ph.x;
-          sh.scal[3] = ph.y;
-        }
-        load_filtered(X, a.N, (int)sh.P[h].bin, a.resp + (long long)c * NDEC, false, v);
+        stage_filtered<false>(X, a.N, (int)sh.P[h].bin, a.resp + (long long)c * NDEC, sh.buf);
       } else if (job == 2) {
         if (!filtered) break;
         // REAL overlap-save input of the post-detection filter, L=olen, M=NDEC-olen+1 (fm.c:39-43): two real channels
         // ride one complex transform, z = audA + j audB (the filter's impulse response is real). History lives in a
         // 2048-sample ring per channel; this block's new samples are appended to it here.
         const int ringbase = (int)(((m + 1) * (long long)olen) & (NDEC - 1));
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-#pragma unroll
-          for (int r = 0; r < 8; r++) {
-            const int p = t + 128 * e + 256 * r;
-            const int ri = (ringbase + p) & (NDEC - 1);
-            float2 z;
-            if (p < first) {
-              z.x = hist[0][ri];
-              z.y = hist[1] ? hist[1][ri] : 0.f;
-            } else {
-              z.x = sh.aux0[p - first];
-              z.y = sh.aux1[p - first];
-              hist[0][ri] = z.x;
-              if (hist[1]) hist[1][ri] = z.y;
-            }
-            v[8 * e + r] = make_float2(z.x, -z.y);  // conj: forward transform through the backward code
+#pragma unroll 2
+        for (int p = t; p < NDEC; p += FFT2048_THREADS) {
+          const int ri = (ringbase + p) & (NDEC - 1);
+          float2 z;
+          if (p < first) {
+            z.x = hist[0][ri];
+            z.y = hist[1] ? hist[1][ri] : 0.f;
+          } else {
+            z.x = sh.aux0[p - first];
+            z.y = sh.aux1[p - first];
+            hist[0][ri] = z.x;
+            if (hist[1]) hist[1][ri] = z.y;
           }
+          sh.buf[p] = make_float2(z.x, -z.y);  // conj: forward transform through the backward code
         }
+      }
+      if (job < 3) {
+        __syncthreads();
+        load16(v, sh.buf);
       }
       fft2048<+1>(v, sh.buf, a.tw2048);
       if (job < 2) {
         float ssq, samp;
-        keep_output(a, sh, v, make_float2(sh.scal[2], sh.scal[3]), c, b, &ssq, &samp);
+        const int e = sh.ephase[h];
+        __syncthreads();  // every thread has read its stage-3 inputs; the buffer can take the output
+        store16(v, sh.buf, jb);
+        phase_and_stats(sh.buf, first, phase_from_index(a, e), &ssq, &samp);
         fm_discriminate(a, sh, h, c, b, ssq, samp, h ? sh.aux1 : sh.aux0);
+        if (t == 0) sh.ephase[h] = phase_advance(e, sh.P[h].phase_step, a.N);
       } else if (job == 2) {
-        const float2* R = a.audio_resp + (long long)sh.P[0].audio_slot * NDEC;
+        const float2* R = a.audio_resp + (long long)sh.P[0].audio_slot * NDEC + t;
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const float2 Z = make_float2(v[j].x, -v[j].y);  // undo the conj: Z = FFT-(z)
-          v[j] = cmul(Z, __ldg(R + t + 128 * j));
+          v[j] = cmul(Z, __ldg(R + 128 * j));
         }
         fft2048_out_to_in(v);
       } else {
         const float gA = sh.P[0].fm_gain, gB = sh.P[1].fm_gain;
-        const int offA = sh.P[0].pcm_off, offB = sh.P[1].pcm_off;
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const int n = t + 128 * j;
+        int16_t* pa = pcm_row + sh.P[0].pcm_off - first;
+        int16_t* pb = pcm_row + sh.P[1].pcm_off - first;
+        const bool haveB = wk.y >= 0;
+        __syncthreads();
+        store16(v, sh.buf, jb);
+        // each thread converts the samples it stored itself (n = t + 128j): no barrier needed in between
+#pragma unroll 2
+        for (int n = t + 128 * jb; n < NDEC; n += FFT2048_THREADS) {
           if (n >= first) {
-            const int o = n - first;
-            pcm_row[offA + o] = scaleclip(v[j].x * gA);  // fm.c:169-170
-            if (wk.y >= 0) pcm_row[offB + o] = scaleclip(v[j].y * gB);
+            const float2 z = sh.buf[n];
+            pa[n] = scaleclip(z.x * gA);  // fm.c:169-170
+            if (haveB) pb[n] = scaleclip(z.y * gB);
           }
         }
       }
@@ -355,6 +410,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) fm_kernel(const ChanLaunch
     if (!filtered) {
       // FLAT: raw discriminator output goes out unfiltered and unscaled (fm.c:55,164-172)
       __syncthreads();
+#pragma unroll 1
       for (int o = t; o < olen; o += FFT2048_THREADS) {
         pcm_row[sh.P[0].pcm_off + o] = scaleclip(sh.aux0[o]);
         if (wk.y >= 0) pcm_row[sh.P[1].pcm_off + o] = scaleclip(sh.aux1[o]);
@@ -377,17 +433,26 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) am_kernel(const ChanLaunch
   const ChanParams P = a.params[c];
   ChanState S = a.state[c];
   const int olen = a.olen;
+  const int first = NDEC - olen;
+  const float2* ybuf = sh.buf + first;  // kept samples y[0..olen)
+  int eph = phase_index0(P.bin, a.start0, a.N);
   float2 v[16];
 #pragma unroll 1
   for (int b = 0; b < a.nblocks; b++) {
     float ssq, samp;
-    load_filtered(a.spec + (long long)b * a.spec_stride, a.N, (int)P.bin, a.resp + (long long)c * NDEC, false, v);
-    fft2048<+1>(v, sh.buf, a.tw2048);
-    // envelope detection ignores the block's LO phase, but the captured filter output must carry it
-    keep_output(a, sh, v, block_phase(P.bin, a.block0 + b, a.L, a.M, a.N), c, b, &ssq, &samp);
+    stage_filtered<false>(a.spec + (long long)b * a.spec_stride, a.N, (int)P.bin, a.resp + (long long)c * NDEC, sh.buf);
     __syncthreads();
+    load16(v, sh.buf);
+    fft2048<+1>(v, sh.buf, a.tw2048);
+    __syncthreads();
+    store16(v, sh.buf, first >> 7);
+    // envelope detection ignores the block's LO phase, but the captured filter output must carry it
+    phase_and_stats(sh.buf, first, phase_from_index(a, eph), &ssq, &samp);
+    eph = phase_advance(eph, P.phase_step, a.N);
+    __syncthreads();
+    if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen);
     for (int o = t; o < olen; o += FFT2048_THREADS) {
-      const float2 y = sh.buf[o];
+      const float2 y = ybuf[o];
       sh.aux0[o] = sqrtf(y.x * y.x + y.y * y.y);  // am.c:56-58
     }
     float d0 = 0.f, d1 = 0.f;
@@ -450,18 +515,29 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) linear_kernel(const ChanLa
   const ChanParams P = a.params[c];
   ChanState S = a.state[c];
   const int olen = a.olen;
+  const int first = NDEC - olen;
+  const float2* ybuf = sh.buf + first;  // kept samples y[0..olen)
+  int eph = phase_index0(P.bin, a.start0, a.N);
   float2 v[16];
 #pragma unroll 1
   for (int b = 0; b < a.nblocks; b++) {
     float ssq, samp;
-    load_filtered(a.spec + (long long)b * a.spec_stride, a.N, (int)P.bin, a.resp + (long long)c * NDEC,
-                  (P.flags & CH_ISB) != 0, v);
-    fft2048<+1>(v, sh.buf, a.tw2048);
-    keep_output(a, sh, v, block_phase(P.bin, a.block0 + b, a.L, a.M, a.N), c, b, &ssq, &samp);
+    if (P.flags & CH_ISB)
+      stage_filtered<true>(a.spec + (long long)b * a.spec_stride, a.N, (int)P.bin, a.resp + (long long)c * NDEC, sh.buf);
+    else
+      stage_filtered<false>(a.spec + (long long)b * a.spec_stride, a.N, (int)P.bin, a.resp + (long long)c * NDEC, sh.buf);
     __syncthreads();
+    load16(v, sh.buf);
+    fft2048<+1>(v, sh.buf, a.tw2048);
+    __syncthreads();
+    store16(v, sh.buf, first >> 7);
+    phase_and_stats(sh.buf, first, phase_from_index(a, eph), &ssq, &samp);
+    eph = phase_advance(eph, P.phase_step, a.N);
+    __syncthreads();
+    if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen);
     float sig = 0.f, noi = 0.f, d2 = 0.f;
     for (int o = t; o < olen; o += FFT2048_THREADS) {
-      const float2 y = sh.buf[o];
+      const float2 y = ybuf[o];
       const float rp = y.x * y.x, ip = y.y * y.y;  // linear.c:256-259
       sig += rp;
       noi += ip;
@@ -499,7 +575,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) linear_kernel(const ChanLa
     const bool shifted = P.shift_cycles != 0.0;
     for (int o = t; o < olen; o += FFT2048_THREADS) {
       const float g = sh.aux1[o];
-      const float2 y = sh.buf[o];
+      const float2 y = ybuf[o];
       float2 z = make_float2(y.x * g, y.y * g);  // linear.c:280
       if (shifted) {
         // post-detection shift oscillator (linear.c:283-289, osc.c:39-51): phasor(n) = exp(j*2*pi*f*n), n counted

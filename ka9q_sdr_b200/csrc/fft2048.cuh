@@ -18,13 +18,25 @@
 // conj(FFT(conj x)) for the opposite sign): the unrolled butterflies are ~25 KB of SASS and several copies thrash the
 // instruction cache (measured: stall_no_instruction was the top stall with four inlined copies).
 #pragma once
+#include <math.h>
 #include "fft_regs.cuh"
 
 namespace k9 {
 
 constexpr int FFT2048_THREADS = 128;
 
-// tw: W_2048^a = exp(-2*pi*i*a/2048), a in [0,2048) (forward sign; conjugated here when SIGN=+1)
+// Twiddle table layout (FFT2048_TW_FLOAT2 float2 entries, built by fft2048_fill_twiddles on the host):
+//   [8p + j], p in [0,256), j in [0,8):   W_2048^(p*j)        stage-1 rows, one 64-byte row per butterfly
+//   [2048 + 16p' + j], p' in [0,16), j in [0,16): W_256^(p'*j) stage-2 rows, one 128-byte row per thread
+// Forward sign (exp(-2*pi*i...)); conjugated on use when SIGN=+1. Rows are read with 128-bit loads.
+constexpr int FFT2048_TW_FLOAT2 = 2048 + 256;
+
+template <int SIGN>
+__device__ __forceinline__ float2 tw_mul(float2 a, float wx, float wy) {
+  // a * (wx + i*SIGN'*wy) where the table holds the forward twiddle: conjugate it for the backward transform
+  return SIGN > 0 ? make_float2(a.x * wx + a.y * wy, a.y * wx - a.x * wy) : make_float2(a.x * wx - a.y * wy, a.x * wy + a.y * wx);
+}
+
 template <int SIGN>
 __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb, const float2* __restrict__ tw) {
   const int t = threadIdx.x;
@@ -32,55 +44,80 @@ __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb
 #pragma unroll
   for (int e = 0; e < 2; e++) {
     Dft<8, SIGN>::run(&v[8 * e]);
-    const int p = t + 128 * e;
+    const float4* row = reinterpret_cast<const float4*>(tw + 8 * (t + 128 * e));
 #pragma unroll
-    for (int j = 1; j < 8; j++) {
-      float2 w = __ldg(tw + ((p * j) & 2047));
-      if (SIGN > 0) w.y = -w.y;
-      v[8 * e + j] = cmul(v[8 * e + j], w);
+    for (int jj = 0; jj < 4; jj++) {
+      const float4 w = __ldg(row + jj);
+      if (jj > 0) v[8 * e + 2 * jj] = tw_mul<SIGN>(v[8 * e + 2 * jj], w.x, w.y);
+      v[8 * e + 2 * jj + 1] = tw_mul<SIGN>(v[8 * e + 2 * jj + 1], w.z, w.w);
     }
   }
   __syncthreads();  // WAR: previous users of the buffer are done
   {
+    // a = 8p + j, swizzled a ^ (t & 15): only the low nibble changes, so per j one XOR on a 3-bit value
     const int sw = t & 15;
+    float2* wp = sb + ((8 * t) & ~15) + ((((t & 1) << 3)) ^ (sw & 8));
+    const int s7 = sw & 7;
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int a = 8 * (t + 128 * e) + j;
-        sb[a ^ sw] = v[8 * e + j];
-      }
+    for (int j = 0; j < 8; j++) {
+      const int off = j ^ s7;
+      wp[off] = v[j];
+      wp[off + 1024] = v[8 + j];
     }
   }
   __syncthreads();
   // ---- stage 2: radix 16 on n=256, s=8: thread t = q + 8p'; reads y1[t + 128 r] ----
   {
-    const int sw = t >> 3;
+    const float2* rp = sb + (t ^ (t >> 3));
 #pragma unroll
-    for (int r = 0; r < 16; r++) v[r] = sb[(t + 128 * r) ^ sw];
+    for (int r = 0; r < 16; r++) v[r] = rp[128 * r];
   }
   Dft<16, SIGN>::run(v);
   {
-    const int pp = t >> 3;  // p'
+    const float4* row = reinterpret_cast<const float4*>(tw + 2048 + 16 * (t >> 3));
 #pragma unroll
-    for (int j = 1; j < 16; j++) {
-      float2 w = __ldg(tw + 8 * pp * j);
-      if (SIGN > 0) w.y = -w.y;
-      v[j] = cmul(v[j], w);
+    for (int jj = 0; jj < 8; jj++) {
+      const float4 w = __ldg(row + jj);
+      if (jj > 0) v[2 * jj] = tw_mul<SIGN>(v[2 * jj], w.x, w.y);
+      v[2 * jj + 1] = tw_mul<SIGN>(v[2 * jj + 1], w.z, w.w);
     }
   }
   __syncthreads();  // WAR on the buffer
   {
-    const int q = t & 7, pp = t >> 3;
-    const int base = (q + 128 * pp) ^ ((pp & 1) << 3);
+    // a = q + 128 p' + 8 j (no carries), swizzled by bit 3 when p' is odd: a' = (q + 128 p') + 8*(j ^ (p'&1))
+    const int pp = t >> 3;
+    float2* wp = sb + (t & 7) + 128 * pp;
+    const int sbit = pp & 1;
 #pragma unroll
-    for (int j = 0; j < 16; j++) sb[base ^ (8 * j)] = v[j];  // a = q + 128 p' + 8 j (no carries), swizzled
+    for (int j = 0; j < 16; j++) wp[8 * (j ^ sbit)] = v[j];
   }
   __syncthreads();
   // ---- stage 3: radix 16 on n=16, s=128: thread t reads y2[t + 128 r], writes X[t + 128 j] ----
+  {
+    const float2* rp0 = sb + t;        // even r: no swizzle
+    const float2* rp1 = sb + (t ^ 8);  // odd r: bit 3 flipped
 #pragma unroll
-  for (int r = 0; r < 16; r++) v[r] = sb[(t + 128 * r) ^ ((r & 1) << 3)];
+    for (int r = 0; r < 16; r += 2) {
+      v[r] = rp0[128 * r];
+      v[r + 1] = rp1[128 * (r + 1)];
+    }
+  }
   Dft<16, SIGN>::run(v);
+}
+
+// Host-side table builder (double precision, rounded once)
+inline void fft2048_fill_twiddles(float2* tw) {
+  const double pi = 3.14159265358979323846;
+  for (int p = 0; p < 256; p++)
+    for (int j = 0; j < 8; j++) {
+      const double ang = -2.0 * pi * (double)((p * j) % 2048) / 2048.0;
+      tw[8 * p + j] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+  for (int pp = 0; pp < 16; pp++)
+    for (int j = 0; j < 16; j++) {
+      const double ang = -2.0 * pi * (double)((pp * j) % 256) / 256.0;
+      tw[2048 + 16 * pp + j] = make_float2((float)cos(ang), (float)sin(ang));
+    }
 }
 
 // Register permutation: output layout (index j) -> input layout (index 8e + r) with j = e + 2r.

@@ -56,3 +56,19 @@ void renorm_osc(struct osc *o) {
   if (o->rate != 0)
     o->phasor_step /= cabs(o->phasor_step);
 }
+
+/* Test/diagnostic helper: set_osc(f, r) on a fresh oscillator, then n step_osc() results as (re, im) doubles. */
+int ka9q_osc_run(double f, double r, long n, double *out) {
+  struct osc o = {0};
+  if (!out || n < 0)
+    return -1;
+  pthread_mutex_init(&o.mutex, NULL);
+  set_osc(&o, f, r);
+  for (long i = 0; i < n; i++) {
+    complex double const v = step_osc(&o);
+    out[2 * i] = creal(v);
+    out[2 * i + 1] = cimag(v);
+  }
+  pthread_mutex_destroy(&o.mutex);
+  return 0;
+}

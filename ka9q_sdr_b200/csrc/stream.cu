@@ -14,6 +14,7 @@
 #include "bigfft.cuh"
 #include "chan.cuh"
 #include "design.cuh"
+#include "fft2048.cuh"
 #include "util.cuh"
 
 namespace k9 {
@@ -343,13 +344,10 @@ int ka9q_stream_commit(ka9q_stream* s) {
   if (s->fwd.npass >= 3) K9_CUDA(cudaMalloc(&s->d_tmp1, sizeof(float2) * (size_t)B * N));
   K9_CUDA(cudaMalloc(&s->d_energy, sizeof(float) * B));
   {
-    std::vector<float2> tw(NDEC);
-    for (int a = 0; a < NDEC; a++) {
-      double ang = -2.0 * M_PI * a / NDEC;
-      tw[a] = make_float2((float)cos(ang), (float)sin(ang));
-    }
-    K9_CUDA(cudaMalloc(&s->d_tw2048, sizeof(float2) * NDEC));
-    K9_CUDA(cudaMemcpy(s->d_tw2048, tw.data(), sizeof(float2) * NDEC, cudaMemcpyHostToDevice));
+    std::vector<float2> tw(FFT2048_TW_FLOAT2);
+    fft2048_fill_twiddles(tw.data());
+    K9_CUDA(cudaMalloc(&s->d_tw2048, sizeof(float2) * tw.size()));
+    K9_CUDA(cudaMemcpy(s->d_tw2048, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
   }
   // per-channel arrays
   K9_CUDA(cudaMalloc(&s->d_resp, sizeof(float2) * (size_t)K * NDEC));
@@ -380,6 +378,7 @@ int ka9q_stream_commit(ka9q_stream* s) {
     off += (long long)s->olen * p.channels;
     P.headroom = p.headroom;
     P.audio_slot = -1;
+    P.phase_step = (int)((p.bin % N) * (long long)(L % N) % N);
     float const samptime = (float)s->cfg.decimate / (float)s->cfg.samprate;
     if (p.demod_type == KA9Q_FM_DEMOD) {
       any_fm = true;
@@ -516,6 +515,14 @@ static void fill_launch(ka9q_stream* s, ChanLaunch& a, int nblocks) {
   a.dsamprate = (float)s->cfg.samprate / s->cfg.decimate;
   a.nblocks = nblocks;
   a.block0 = s->phase_block;
+  {
+    long long st0 = (s->phase_block % s->N) * (long long)(s->cfg.L % s->N) % s->N - (long long)((s->cfg.M - 1) % s->N);
+    st0 %= s->N;
+    if (st0 < 0) st0 += s->N;
+    a.start0 = (int)st0;
+  }
+  a.twN_lo = s->fwd.tw_lo;
+  a.twN_hi = s->fwd.tw_hi;
   a.tw2048 = s->d_tw2048;
   a.params = s->d_params;
   a.state = s->d_state;
