@@ -80,19 +80,47 @@ template <bool ISB>
 __device__ __forceinline__ void stage_filtered(const float2* __restrict__ X, int N, int bin,
                                                const float2* __restrict__ H, float2* __restrict__ buf) {
   const int t = threadIdx.x;
-#pragma unroll 4
-  for (int k = 0; k < 16; k++) {
-    const int p = t + 128 * k;
-    float2 y = cmul(__ldg(H + p), load_bin(X, N, bin, p));
-    if (ISB && p != 0 && p != NDEC / 2) {
-      const int pm = NDEC - p;
-      const float2 ym = cmul(__ldg(H + pm), load_bin(X, N, bin, pm));
-      if (p < NDEC / 2)
-        y = make_float2(y.x + ym.x, y.y - ym.y);  // pos + conj(neg)
-      else
-        y = make_float2(y.x - ym.x, y.y + ym.y);  // neg - conj(pos)
+  if (!ISB) {
+    // two halves of 8 elements; within a half the spectrum index just steps by 128 (one wrap test each), and all 16
+    // loads of the half are in flight before the first product is formed
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+      // half 0: p = t + 128k (k<8) -> s = p;  half 1: p = t + 1024 + 128k -> s = p - 2048, except p == 1024 (s = +1024)
+      int idx = bin + t + (half ? -1024 : 0);
+      if (idx < 0) idx += N;
+      if (idx >= N) idx -= N;
+      float2 x[8], h[8];
+      const float2* Hp = H + t + 1024 * half;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        int i = idx + 128 * k;
+        if (i >= N) i -= N;
+        if (half && k == 0 && t == 0) {  // the Nyquist bin belongs to the positive side (filter.c:206: p <= N_dec/2)
+          i = bin + 1024;
+          if (i >= N) i -= N;
+        }
+        x[k] = __ldg(X + i);
+        h[k] = __ldg(Hp + 128 * k);
+      }
+      float2* bp = buf + t + 1024 * half;
+#pragma unroll
+      for (int k = 0; k < 8; k++) bp[128 * k] = cmul(h[k], x[k]);
     }
-    buf[p] = y;
+  } else {
+#pragma unroll 2
+    for (int k = 0; k < 16; k++) {
+      const int p = t + 128 * k;
+      float2 y = cmul(__ldg(H + p), load_bin(X, N, bin, p));
+      if (p != 0 && p != NDEC / 2) {
+        const int pm = NDEC - p;
+        const float2 ym = cmul(__ldg(H + pm), load_bin(X, N, bin, pm));
+        if (p < NDEC / 2)
+          y = make_float2(y.x + ym.x, y.y - ym.y);  // pos + conj(neg)
+        else
+          y = make_float2(y.x - ym.x, y.y + ym.y);  // neg - conj(pos)
+      }
+      buf[p] = y;
+    }
   }
 }
 
@@ -152,6 +180,10 @@ __device__ __noinline__ void dump_filter_output(float2* dst, const float2* src, 
 
 // ---------------------------------------------------------------- FM (pairs)
 
+#ifndef FM_CTAS_PER_SM
+#define FM_CTAS_PER_SM 8  // 64 registers/thread, 8 x 25 KB shared memory
+#endif
+
 // index of the last good sample strictly below o, or -1
 __device__ __forceinline__ int prev_good(const unsigned* good, int o) {
   int w = o >> 5;
@@ -163,11 +195,36 @@ __device__ __forceinline__ int prev_good(const unsigned* good, int o) {
   }
 }
 
-__device__ __noinline__ float fm_arg(float2 y, float2 st) {
+// atan2 for the discriminator: octant reduction + degree-8 minimax polynomial in (min/max)^2, max abs error 9e-8 rad
+// before the final pi/2, pi reflections (fitted against float64 atan over [0,1]; the discriminator output is scaled by
+// ~5.6e3 LSB/rad, so this is < 1e-3 LSB). Zero / non-finite arguments take libm's atan2f so the special values
+// (e.g. state == 0 right after the squelch opens, fm.c:156) follow IEEE exactly as the reference's cargf does.
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  if (!(mx > 0.f && mx < 1e30f)) return atan2f(y, x);
+  const float a = __fdividef(mn, mx);
+  const float s = a * a;
+  float p = 0.002456682501360774f;
+  p = fmaf(p, s, -0.014401180669665337f);
+  p = fmaf(p, s, 0.03978091850876808f);
+  p = fmaf(p, s, -0.07234828919172287f);
+  p = fmaf(p, s, 0.10498931258916855f);
+  p = fmaf(p, s, -0.141612246632576f);
+  p = fmaf(p, s, 0.19985906779766083f);
+  p = fmaf(p, s, -0.33332598209381104f);
+  p = fmaf(p, s, 0.9999998807907104f);
+  float r = p * a;
+  if (ay > ax) r = 1.57079637f - r;
+  if (x < 0.f) r = 3.14159274f - r;
+  return copysignf(r, y);
+}
+
+__device__ __forceinline__ float fm_arg(float2 y, float2 st) {
   // cargf(samp * state) (fm.c:131)
   const float re = y.x * st.x - y.y * st.y;
   const float im = y.x * st.y + y.y * st.x;
-  return atan2f(im, re);
+  return fast_atan2f(im, re);
 }
 
 // Squelch + discriminator for one channel-block whose kept samples are in sh.buf (fm.c:86-160). Writes olen audio
@@ -308,7 +365,7 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
   }
 }
 
-__global__ void __launch_bounds__(FFT2048_THREADS, 5) fm_kernel(const ChanLaunch a) {
+__global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(const ChanLaunch a) {
   __shared__ CtaShared sh;
   const int t = threadIdx.x;
   const int2 wk = a.work[blockIdx.x];
@@ -352,20 +409,36 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 5) fm_kernel(const ChanLaunch
         // ride one complex transform, z = audA + j audB (the filter's impulse response is real). History lives in a
         // 2048-sample ring per channel; this block's new samples are appended to it here.
         const int ringbase = (int)(((m + 1) * (long long)olen) & (NDEC - 1));
-#pragma unroll 2
-        for (int p = t; p < NDEC; p += FFT2048_THREADS) {
-          const int ri = (ringbase + p) & (NDEC - 1);
-          float2 z;
-          if (p < first) {
-            z.x = hist[0][ri];
-            z.y = hist[1] ? hist[1][ri] : 0.f;
-          } else {
-            z.x = sh.aux0[p - first];
-            z.y = sh.aux1[p - first];
-            hist[0][ri] = z.x;
-            if (hist[1]) hist[1][ri] = z.y;
+        // history rows (p < first): all ring loads in flight first (v[] is dead here, registers are free)
+        {
+          float ha[9], hb[9];
+#pragma unroll
+          for (int k = 0; k < 9; k++) {
+            const int p = t + 128 * k;
+            const int ri = (ringbase + p) & (NDEC - 1);
+            const bool use = p < first;
+            ha[k] = use ? hist[0][ri] : 0.f;
+            hb[k] = (use && hist[1]) ? hist[1][ri] : 0.f;
           }
-          sh.buf[p] = make_float2(z.x, -z.y);  // conj: forward transform through the backward code
+#pragma unroll
+          for (int k = 0; k < 9; k++) {
+            const int p = t + 128 * k;
+            if (p < first) sh.buf[p] = make_float2(ha[k], -hb[k]);  // conj: forward transform via the backward code
+          }
+        }
+#pragma unroll 1
+        for (int p = t + 128 * 9; p < first; p += FFT2048_THREADS) {  // only when olen < 896
+          const int ri = (ringbase + p) & (NDEC - 1);
+          sh.buf[p] = make_float2(hist[0][ri], hist[1] ? -hist[1][ri] : 0.f);
+        }
+        // new samples: append to the ring and stage
+#pragma unroll 2
+        for (int o = t; o < olen; o += FFT2048_THREADS) {
+          const int ri = (ringbase + first + o) & (NDEC - 1);
+          const float za = sh.aux0[o], zb = sh.aux1[o];
+          hist[0][ri] = za;
+          if (hist[1]) hist[1][ri] = zb;
+          sh.buf[first + o] = make_float2(za, -zb);
         }
       }
       if (job < 3) {
@@ -618,6 +691,13 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) linear_kernel(const ChanLa
 
 int launch_fm(const ChanLaunch& a, cudaStream_t st) {
   if (a.nwork <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(fm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(am_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(linear_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
   fm_kernel<<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

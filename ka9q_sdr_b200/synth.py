@@ -107,32 +107,32 @@ def multi_channel(samprate: int, nblocks: int, bins, modes, seed: int, amplitude
 
 
 def comb_spectrum_iq(samprate: int, nblocks: int, bins, seed: int, amplitude: float, sigma: float,
-                     tone0: float = 400.0, tone_step: float = 10.0, deviation: float = 1500.0, dtype=np.float32):
-    """Cheap wide-band stimulus for the throughput configs (thousands of channels, tens of MS/s):
-    each channel's FM signal is synthesised at the 48 kHz channel rate and the multiplex is built with one
-    inverse FFT per block-sized chunk (a frequency-domain comb), so cost is O(samples log samples), not
-    O(channels * samples). Block-edge discontinuities are irrelevant to a throughput/invariance stimulus;
-    parity cases use multi_channel() instead."""
+                     tone0: float = 400.0, tone_step: float = 50.0, deviation: float = 1500.0):
+    """Cheap wide-band stimulus for the throughput configs (thousands of channels, tens of MS/s).
+
+    Every channel carries a continuous, phase-coherent NBFM signal: the modulating tones are multiples of the block
+    rate (50 Hz) and the carriers sit on the L-point grid (multiples of Fs/L = 50 Hz, i.e. within 25 Hz of the channel
+    centre bin*Fs/N), so the whole multiplex is exactly periodic in one block. It is therefore synthesised once, in
+    the frequency domain (one 960-point FFT per channel placed around its carrier, one L-point inverse FFT: cost
+    O(samples log samples), not O(channels * samples)), and repeated for every block with fresh AWGN on top.
+    Parity cases use multi_channel() (time-domain synthesis on the exact bin grid) instead."""
     fs = samprate
     D, L, M, N = geometry(fs)
     rng = np.random.default_rng(seed)
-    n = nblocks * L
-    out = np.empty(2 * n, dtype=np.int16)
     olen = L // D
     t48 = np.arange(olen, dtype=np.float64) / (fs / D)
+    spec = np.zeros(L, dtype=np.complex128)
+    h = olen // 2
+    for j, k in enumerate(bins):
+        tone = tone0 + tone_step * (j % 32)
+        ph = (deviation / tone) * np.sin(2 * np.pi * tone * t48) + 0.61 * j
+        S = np.fft.fft(np.exp(1j * ph))
+        kc = int(round(k * L / N))
+        idx = (kc + np.arange(-h, h)) % L
+        spec[idx] += np.concatenate([S[-h:], S[:h]]) * (amplitude * D)
+    clean = np.fft.ifft(spec).astype(np.complex64)
+    out = np.empty(2 * nblocks * L, dtype=np.int16)
     for b in range(nblocks):
-        spec = np.zeros(L, dtype=np.complex64)
-        for j, k in enumerate(bins):
-            tone = tone0 + tone_step * (j % 64)
-            ph = (deviation / tone) * np.sin(2 * np.pi * tone * (t48 + b * olen / (fs / D)))
-            s = np.exp(1j * ph).astype(np.complex64)
-            S = np.fft.fft(s)
-            # place the olen-bin baseband spectrum around the carrier bin of an L-point grid
-            kc = int(round(k * L / N))
-            h = olen // 2
-            idx = (kc + np.arange(-h, h)) % L
-            spec[idx] += np.concatenate([S[-h:], S[:h]]) * (amplitude * D)
-        x = np.fft.ifft(spec).astype(np.complex64) * 1.0
-        x = x + (sigma * (rng.standard_normal(L) + 1j * rng.standard_normal(L))).astype(np.complex64)
+        x = clean + (sigma * (rng.standard_normal(L) + 1j * rng.standard_normal(L))).astype(np.complex64)
         out[2 * b * L:2 * (b + 1) * L] = _quantize(x)
     return dict(samprate=fs, D=D, L=L, M=M, N=N, iq=out, bins=list(bins))
