@@ -107,7 +107,7 @@ def multi_channel(samprate: int, nblocks: int, bins, modes, seed: int, amplitude
 
 
 def comb_spectrum_iq(samprate: int, nblocks: int, bins, seed: int, amplitude: float, sigma: float,
-                     tone0: float = 400.0, tone_step: float = 50.0, deviation: float = 1500.0):
+                     tone0: float = 300.0, tone_step: float = 50.0, deviation: float = 1000.0):
     """Cheap wide-band stimulus for the throughput configs (thousands of channels, tens of MS/s).
 
     Every channel carries a continuous, phase-coherent NBFM signal: the modulating tones are multiples of the block
@@ -124,7 +124,7 @@ def comb_spectrum_iq(samprate: int, nblocks: int, bins, seed: int, amplitude: fl
     spec = np.zeros(L, dtype=np.complex128)
     h = olen // 2
     for j, k in enumerate(bins):
-        tone = tone0 + tone_step * (j % 32)
+        tone = tone0 + tone_step * (j % 16)
         ph = (deviation / tone) * np.sin(2 * np.pi * tone * t48) + 0.61 * j
         S = np.fft.fft(np.exp(1j * ph))
         kc = int(round(k * L / N))

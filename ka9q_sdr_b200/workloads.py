@@ -67,7 +67,7 @@ def cfg4(nchan: int = 1024) -> Plan:
 def cfg5(nchan: int = 8192, offset_bins: int = 0) -> Plan:
     """8192 NBFM channels on 61.44 MS/s, 7.03125 kHz raster (300 bins), edges narrowed to +-3 kHz so neighbours do
     not overlap. offset_bins shifts the whole raster (used to give every GPU rank distinct carriers)."""
-    p = _plan("cfg5: 8192x NBFM @61.44 MS/s", 61440000, 5, 0.002, 0.003, 1500.0)
+    p = _plan("cfg5: 8192x NBFM @61.44 MS/s", 61440000, 5, 0.002, 0.003, 1000.0)
     p.channels = [ChannelSpec("FM", 300 * (j - nchan // 2) + offset_bins, -3000.0, 3000.0) for j in range(nchan)]
     return p
 
