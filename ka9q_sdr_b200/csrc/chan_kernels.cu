@@ -32,12 +32,12 @@ struct CtaShared {
   ChanState S[2];
 };
 
-// three block-wide reductions in one round trip: sum(a), sum(b), sum(c) — or sum(a), max(b), min(c) when MINMAX
-template <bool MINMAX>
+// three block-wide reductions in one round trip. MODE 0: sum,sum,sum  1: sum,max,min  2: sum,sum,min
+template <int MODE>
 __device__ __forceinline__ void block_reduce3(float& a, float& b, float& c, float* red) {
   a = warp_sum(a);
-  b = MINMAX ? warp_max(b) : warp_sum(b);
-  c = MINMAX ? warp_min(c) : warp_sum(c);
+  b = MODE == 1 ? warp_max(b) : warp_sum(b);
+  c = MODE == 0 ? warp_sum(c) : warp_min(c);
   __syncthreads();  // protect red[] from the previous use
   const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
@@ -47,13 +47,8 @@ __device__ __forceinline__ void block_reduce3(float& a, float& b, float& c, floa
   }
   __syncthreads();
   a = (red[0] + red[1]) + (red[2] + red[3]);
-  if (MINMAX) {
-    b = fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]));
-    c = fminf(fminf(red[8], red[9]), fminf(red[10], red[11]));
-  } else {
-    b = (red[4] + red[5]) + (red[6] + red[7]);
-    c = (red[8] + red[9]) + (red[10] + red[11]);
-  }
+  b = MODE == 1 ? fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])) : (red[4] + red[5]) + (red[6] + red[7]);
+  c = MODE == 0 ? (red[8] + red[9]) + (red[10] + red[11]) : fminf(fminf(red[8], red[9]), fminf(red[10], red[11]));
 }
 
 // float -> int16 as audio.c:22-28: clip, then C truncation toward zero of 32767*x
@@ -152,30 +147,34 @@ __device__ __forceinline__ int phase_advance(int e, int step, int N) {
   return e >= N ? e - N : e;
 }
 
-// After the inverse transform (output already in buf, natural order): apply the block phase in place to the kept
-// samples n in [first, NDEC) and return this thread's partial sums of |y|^2 and |y|. Each thread touches only the
-// elements it stored itself (n = t + 128j), so no barrier is needed between store16 and this.
-__device__ __forceinline__ void phase_and_stats(float2* __restrict__ buf, int first, float2 ph, float* sumsq, float* sumamp) {
-  float ssq = 0.f, samp = 0.f;
-#pragma unroll 2
+// After the inverse transform (output already in buf, natural order): this thread's partial sums of |y|^2 and |y| and
+// its minimum |y|^2 over the kept samples n in [first, NDEC). Each thread reads only the elements it stored itself
+// (n = t + 128j), so no barrier is needed between store16 and this. The per-block LO phase (Appendix C) is NOT applied
+// here: |y| does not depend on it; the consumers that do (discriminator state across blocks, linear output, the debug
+// capture) apply it themselves, once per block or fused into a multiply they already do.
+__device__ __forceinline__ void kept_stats(const float2* __restrict__ buf, int first, float* sumsq, float* sumamp,
+                                           float* minsq) {
+  float ssq = 0.f, samp = 0.f, mn = INFINITY;
+#pragma unroll 4
   for (int n = threadIdx.x + 128 * (first >> 7); n < NDEC; n += 128) {
     if (n >= first) {
-      const float2 y = cmul(buf[n], ph);
-      buf[n] = y;
+      const float2 y = buf[n];
       const float q = y.x * y.x + y.y * y.y;
       ssq += q;
+      mn = fminf(mn, q);
       // |y| for the squelch statistics only (fm.c:95): MUFU.RSQ based, ~1 ulp; it only feeds threshold decisions
       samp += (q > 0.f) ? q * rsqrtf(q) : 0.f;
     }
   }
   *sumsq = ssq;
   *sumamp = samp;
+  *minsq = mn;
 }
 
 // optional raw filter-output capture for the parity tests (off the hot path)
-__device__ __noinline__ void dump_filter_output(float2* dst, const float2* src, int olen) {
+__device__ __noinline__ void dump_filter_output(float2* dst, const float2* src, int olen, float2 ph) {
 #pragma unroll 1
-  for (int o = threadIdx.x; o < olen; o += FFT2048_THREADS) dst[o] = src[o];
+  for (int o = threadIdx.x; o < olen; o += FFT2048_THREADS) dst[o] = cmul(src[o], ph);
 }
 
 // ---------------------------------------------------------------- FM (pairs)
@@ -227,16 +226,17 @@ __device__ __forceinline__ float fm_arg(float2 y, float2 st) {
   return fast_atan2f(im, re);
 }
 
-// Squelch + discriminator for one channel-block whose kept samples are in sh.buf (fm.c:86-160). Writes olen audio
-// samples to aud[], updates sh.S[h] and the status row.
+// Squelch + discriminator for one channel-block whose kept samples (without the block's LO phase ph) are in sh.buf
+// (fm.c:86-160). Writes olen audio samples to aud[], updates sh.S[h] and the status row. The discriminator only sees
+// phase differences, so ph enters once: the carried state conj(last good sample) is kept in the true (rotated) domain
+// and moved into / out of this block's unrotated domain with one complex multiply each way.
 __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& sh, int h, int c, int b, float ssq,
-                                                float samp, float* __restrict__ aud) {
+                                                float samp, float minsq, float2 ph, float* __restrict__ aud) {
   const int t = threadIdx.x;
   const int olen = a.olen;
   const float2* ybuf = sh.buf + (NDEC - olen);  // kept samples y[0..olen)
-  float dummy = 0.f;
-  block_reduce3<false>(ssq, samp, dummy, sh.red);
-  if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen);
+  block_reduce3<2>(ssq, samp, minsq, sh.red);
+  if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen, ph);
   const float bb_power = ssq / (2 * olen);
   const float avg_amp = samp / ((float)M_SQRT2 * olen);
   const float fm_variance = bb_power - avg_amp * avg_amp;
@@ -253,87 +253,78 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
   float new_last = 0.f, foffset = sh.S[h].fm_foffset, pdeviation = sh.S[h].fm_pdeviation;
   if (open) {
     const float min_ampl = 0.55f * 0.55f * avg_amp * avg_amp;  // fm.c:121
-    const float2 old_state = sh.S[h].fm_state;
+    const float2 old_state = cmul(sh.S[h].fm_state, ph);       // into this block's unrotated domain
     const float old_last = sh.S[h].fm_lastaudio;
-    // good-sample flags: one ballot per 32 samples; all_good short-cuts the common case of a clean block
-    bool mine_good = true;
+    const bool all_good = minsq > min_ampl;  // every sample passes the blanking threshold (the usual case)
+    if (!all_good) {
+      // good-sample bitmap, one ballot per 32 samples
+#pragma unroll 2
+      for (int i = 0; i < 8; i++) {
+        const int o = t + 128 * i;
+        bool g = false;
+        if (o < olen) {
+          const float2 y = ybuf[o];
+          g = (y.x * y.x + y.y * y.y) > min_ampl;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, g);
+        if ((t & 31) == 0) sh.good[(t >> 5) + 4 * i] = mask;
+      }
+      __syncthreads();
+    }
+    float fsum = 0.f, pos = -INFINITY, neg = INFINITY;
+    const int lane = t & 31;
 #pragma unroll 2
     for (int i = 0; i < 8; i++) {
       const int o = t + 128 * i;
-      bool g = false;
       if (o < olen) {
-        const float2 y = ybuf[o];
-        g = (y.x * y.x + y.y * y.y) > min_ampl;
-        mine_good = mine_good && g;
-      }
-      const unsigned mask = __ballot_sync(0xffffffffu, g);
-      if ((t & 31) == 0) sh.good[(t >> 5) + 4 * i] = mask;
-    }
-    const bool all_good = __syncthreads_and(mine_good);  // also publishes sh.good
-    float fsum = 0.f, pos = -INFINITY, neg = INFINITY;
-    if (all_good) {
-      // every sample passes the blanking threshold: audio[n] = arg(y[n] * conj(y[n-1])) (fm.c:130-132)
-#pragma unroll 2
-      for (int i = 0; i < 8; i++) {
-        const int o = t + 128 * i;
-        if (o < olen) {
-          float2 st = old_state;
+        bool g = true, gp = true;
+        if (!all_good) {
+          const unsigned wbits = sh.good[o >> 5];
+          g = (wbits >> lane) & 1u;
+          gp = lane ? ((wbits >> (lane - 1)) & 1u) : (o ? (sh.good[(o >> 5) - 1] >> 31) : 1u);
+        }
+        // audio[n] = arg(y[src] * conj(y[prev good before src])) (fm.c:130-132,141): src = n when n is good
+        float2 ys = ybuf[o], st = old_state;  // old_state is already conj(previous block's last good sample)
+        bool have = true, cj = false;
+        if (g && gp) {
           if (o > 0) {
             st = ybuf[o - 1];
-            st.y = -st.y;
+            cj = true;
           }
-          const float audio = fm_arg(ybuf[o], st);
-          aud[o] = audio;
-          fsum += audio;
-          if (o > 0) {
-            pos = fmaxf(pos, audio);
-            neg = fminf(neg, audio);
-          } else {
-            sh.scal[0] = audio;
-          }
-          if (o == olen - 1) sh.scal[1] = audio;
-        }
-      }
-    } else {
-#pragma unroll 1
-      for (int i = 0; i < 8; i++) {
-        const int o = t + 128 * i;
-        if (o < olen) {
-          const bool g = (sh.good[o >> 5] >> (o & 31)) & 1u;
-          const int src = g ? o : prev_good(sh.good, o);  // sample whose discriminator value is emitted
-          float audio;
-          if (src < 0) {
-            audio = old_last;  // no good sample yet in this block: repeat the carried one (fm.c:141)
-          } else {
+        } else {
+          const int src = g ? o : prev_good(sh.good, o);
+          have = src >= 0;  // no good sample yet in this block: repeat the carried audio value
+          if (have) {
+            ys = ybuf[src];
             const int pg = prev_good(sh.good, src);
-            float2 st = old_state;
             if (pg >= 0) {
               st = ybuf[pg];
-              st.y = -st.y;
+              cj = true;
             }
-            audio = fm_arg(ybuf[src], st);
           }
-          aud[o] = audio;
-          fsum += audio;
-          if (g && o > 0) {
-            pos = fmaxf(pos, audio);
-            neg = fminf(neg, audio);
-          }
-          if (o == 0) sh.scal[0] = g ? audio : 0.f;
-          if (o == olen - 1) sh.scal[1] = audio;
         }
+        if (cj) st.y = -st.y;
+        const float audio = have ? fm_arg(ys, st) : old_last;
+        aud[o] = audio;
+        fsum += audio;
+        if (g && o > 0) {
+          pos = fmaxf(pos, audio);
+          neg = fminf(neg, audio);
+        }
+        if (o == 0) sh.scal[0] = g ? audio : 0.f;
+        if (o == olen - 1) sh.scal[1] = audio;
       }
     }
-    block_reduce3<true>(fsum, pos, neg, sh.red);
+    block_reduce3<1>(fsum, pos, neg, sh.red);
     const float init = sh.scal[0];
     const float pdev_pos = fmaxf(pos, init);
     const float pdev_neg = fminf(neg, init);
     const float avg_f = fsum / olen;
     const int lg = all_good ? olen - 1 : prev_good(sh.good, olen);
-    new_state = old_state;
+    new_state = sh.S[h].fm_state;
     if (lg >= 0) {
-      new_state = ybuf[lg];
-      new_state.y = -new_state.y;
+      const float2 yl = ybuf[lg];
+      new_state = cmul(make_float2(yl.x, -yl.y), make_float2(ph.x, -ph.y));  // conj(y * ph): back to the true domain
     }
     new_last = sh.scal[1];
     if (below < 1) {  // frequency offset and peak deviation only while fully open (fm.c:145-154)
@@ -447,12 +438,12 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
       }
       fft2048<+1>(v, sh.buf, a.tw2048);
       if (job < 2) {
-        float ssq, samp;
+        float ssq, samp, minsq;
         const int e = sh.ephase[h];
         __syncthreads();  // every thread has read its stage-3 inputs; the buffer can take the output
         store16(v, sh.buf, jb);
-        phase_and_stats(sh.buf, first, phase_from_index(a, e), &ssq, &samp);
-        fm_discriminate(a, sh, h, c, b, ssq, samp, h ? sh.aux1 : sh.aux0);
+        kept_stats(sh.buf, first, &ssq, &samp, &minsq);
+        fm_discriminate(a, sh, h, c, b, ssq, samp, minsq, phase_from_index(a, e), h ? sh.aux1 : sh.aux0);
         if (t == 0) sh.ephase[h] = phase_advance(e, sh.P[h].phase_step, a.N);
       } else if (job == 2) {
         const float2* R = a.audio_resp + (long long)sh.P[0].audio_slot * NDEC + t;
@@ -519,17 +510,19 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) am_kernel(const ChanLaunch
     fft2048<+1>(v, sh.buf, a.tw2048);
     __syncthreads();
     store16(v, sh.buf, first >> 7);
-    // envelope detection ignores the block's LO phase, but the captured filter output must carry it
-    phase_and_stats(sh.buf, first, phase_from_index(a, eph), &ssq, &samp);
-    eph = phase_advance(eph, P.phase_step, a.N);
+    // envelope detection ignores the block's LO phase; only the captured filter output carries it
+    float minsq;
+    kept_stats(sh.buf, first, &ssq, &samp, &minsq);
     __syncthreads();
-    if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen);
+    if (a.filt_dbg)
+      dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen, phase_from_index(a, eph));
+    eph = phase_advance(eph, P.phase_step, a.N);
     for (int o = t; o < olen; o += FFT2048_THREADS) {
       const float2 y = ybuf[o];
       sh.aux0[o] = sqrtf(y.x * y.x + y.y * y.y);  // am.c:56-58
     }
     float d0 = 0.f, d1 = 0.f;
-    block_reduce3<false>(ssq, d0, d1, sh.red);  // includes the barrier publishing aux0
+    block_reduce3<0>(ssq, d0, d1, sh.red);  // includes the barrier publishing aux0
     const float signal = ssq;
     if (t == 0) {
       // strictly serial recurrences: carrier-DC tracker and hang AGC (am.c:60-74); one lane, original operation order
@@ -604,10 +597,12 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) linear_kernel(const ChanLa
     fft2048<+1>(v, sh.buf, a.tw2048);
     __syncthreads();
     store16(v, sh.buf, first >> 7);
-    phase_and_stats(sh.buf, first, phase_from_index(a, eph), &ssq, &samp);
+    float minsq;
+    kept_stats(sh.buf, first, &ssq, &samp, &minsq);
+    const float2 ph = phase_from_index(a, eph);  // applied with the AGC gain below: z = (y * ph) * gain
     eph = phase_advance(eph, P.phase_step, a.N);
     __syncthreads();
-    if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen);
+    if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen, ph);
     float sig = 0.f, noi = 0.f, d2 = 0.f;
     for (int o = t; o < olen; o += FFT2048_THREADS) {
       const float2 y = ybuf[o];
@@ -616,7 +611,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) linear_kernel(const ChanLa
       noi += ip;
       sh.aux0[o] = sqrtf(rp + ip);
     }
-    block_reduce3<false>(sig, noi, d2, sh.red);
+    block_reduce3<0>(sig, noi, d2, sh.red);
     const float signal = sig, noise = noi;
     if (t == 0) {
       // hang AGC (linear.c:269-280): serial, one lane, original operation order
@@ -648,7 +643,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 4) linear_kernel(const ChanLa
     const bool shifted = P.shift_cycles != 0.0;
     for (int o = t; o < olen; o += FFT2048_THREADS) {
       const float g = sh.aux1[o];
-      const float2 y = ybuf[o];
+      const float2 y = cmul(ybuf[o], ph);
       float2 z = make_float2(y.x * g, y.y * g);  // linear.c:280
       if (shifted) {
         // post-detection shift oscillator (linear.c:283-289, osc.c:39-51): phasor(n) = exp(j*2*pi*f*n), n counted
