@@ -72,6 +72,12 @@ def cfg5(nchan: int = 8192, offset_bins: int = 0) -> Plan:
     return p
 
 
+def shard_channels(plan: Plan, rank: int, world: int) -> list[ChannelSpec]:
+    """Channel sharding for multi-GPU runs: channel c -> rank c mod world. Channels are independent after
+    the forward FFT (in the reference they are independent processes), so no channel state ever moves between GPUs."""
+    return [c for i, c in enumerate(plan.channels) if i % world == rank]
+
+
 CONFIGS = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}
 
 # Algorithmic bytes per channel-block (SURVEY §8d / BASELINE.md §2): spectrum window + own response + PCM + carried state

@@ -411,8 +411,8 @@ int ref_filter_run(int L, int M, int decimate, int in_type, int out_type, float 
     if (set_filter(slave, low, high, beta) != 0)
       return -2;
   }
-  if (response_out)
-    memcpy(response_out, slave->response, sizeof(complex float) * rbins);
+  if (response_out) /* set_filter always designs all N_dec bins (filter.c:523); a caller-supplied REAL response has N_dec/2+1 */
+    memcpy(response_out, slave->response, sizeof(complex float) * (response_in ? rbins : N_dec));
   if (noise_gain_out)
     *noise_gain_out = slave->noise_gain;
   int const olen = slave->olen;

@@ -200,7 +200,7 @@ def filter_run(L: int, M: int, decimate: int, in_type: int, out_type: int, x: np
         nblocks = x.size // L
     rbins = N_dec // 2 + 1 if out_type == REAL else N_dec
     out = np.zeros(nblocks * olen, dtype=np.float32 if out_type == REAL else np.complex64)
-    resp_out = np.zeros(rbins, dtype=np.complex64)
+    resp_out = np.zeros(rbins if response is not None else N_dec, dtype=np.complex64)
     ng = C.c_float(0)
     fd = np.zeros(N if in_type != REAL else N // 2 + 1, dtype=np.complex64) if want_fdomain else None
     resp_in = np.ascontiguousarray(response, dtype=np.complex64) if response is not None else None
