@@ -271,7 +271,9 @@ int execute_filter_output(struct filter_out* const slave) {
   cudaSetDevice(m->device);
   cudaStream_t st = m->st;
   const int out_type = slave->out_type;  // may be rewritten by the caller between blocks (linear.c:117-120)
-  const int rbins = (out_type == REAL) ? N_dec / 2 + 1 : N_dec;
+  // bins the multiply reads: REAL->REAL only touches the positive half (filter.c:206-208); every other combination
+  // reads response[N_dec/2+1 .. N_dec) too (filter.c:214-216,225-227,232-234)
+  const int rbins = (out_type == REAL && master->in_type == REAL) ? N_dec / 2 + 1 : N_dec;
   pthread_mutex_lock(&slave->response_mutex);
   if (slave->response == NULL) {
     pthread_mutex_unlock(&slave->response_mutex);

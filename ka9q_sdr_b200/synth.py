@@ -119,13 +119,15 @@ def comb_spectrum_iq(samprate: int, nblocks: int, bins, seed: int, amplitude: fl
     fs = samprate
     D, L, M, N = geometry(fs)
     rng = np.random.default_rng(seed)
+    prng = np.random.default_rng(seed + 1000)
     olen = L // D
     t48 = np.arange(olen, dtype=np.float64) / (fs / D)
     spec = np.zeros(L, dtype=np.complex128)
     h = olen // 2
     for j, k in enumerate(bins):
         tone = tone0 + tone_step * (j % 16)
-        ph = (deviation / tone) * np.sin(2 * np.pi * tone * t48) + 0.61 * j
+        # random carrier and modulation phases keep the crest factor of the multiplex Gaussian-like (no clipping)
+        ph = (deviation / tone) * np.sin(2 * np.pi * tone * t48 + prng.uniform(0, 2 * np.pi)) + prng.uniform(0, 2 * np.pi)
         S = np.fft.fft(np.exp(1j * ph))
         kc = int(round(k * L / N))
         idx = (kc + np.arange(-h, h)) % L
