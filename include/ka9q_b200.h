@@ -238,6 +238,9 @@ int ka9q_stream_compute(ka9q_stream *s, int nblocks);
 int ka9q_stream_compute_resident(ka9q_stream *s, int nblocks);
 int ka9q_stream_fetch(ka9q_stream *s, int nblocks, int16_t *pcm, ka9q_chan_status *status);
 int ka9q_stream_sync(ka9q_stream *s);
+/* wait only for the D2H copies issued by ka9q_stream_fetch (PCM/status are double-buffered on the device, so the next
+ * batch may already be computing): the steady-state loop is push(k+2); compute(k+1); fetch(k); wait_fetch() */
+int ka9q_stream_wait_fetch(ka9q_stream *s);
 /* Time of the device work of the last compute call in milliseconds (CUDA events on the compute stream), and of
  * the dominant (channel) kernels alone. Valid after ka9q_stream_sync. */
 int ka9q_stream_last_timing(ka9q_stream *s, float *total_ms, float *fft_ms, float *chan_ms);

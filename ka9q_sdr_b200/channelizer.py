@@ -155,6 +155,9 @@ class Channelizer:
     def fetch(self, nblocks, pcm_ptr, status_ptr=None):
         _lib.check(self.lib.ka9q_stream_fetch(self.h, nblocks, pcm_ptr, status_ptr), "ka9q_stream_fetch")
 
+    def wait_fetch(self):
+        _lib.check(self.lib.ka9q_stream_wait_fetch(self.h), "ka9q_stream_wait_fetch")
+
     def sync(self):
         _lib.check(self.lib.ka9q_stream_sync(self.h), "ka9q_stream_sync")
 

@@ -78,7 +78,7 @@ struct ka9q_stream {
   // streams / events
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr, s_fm = nullptr, s_am = nullptr, s_lin = nullptr;
   cudaEvent_t e_pushed = nullptr, e_fft0 = nullptr, e_fft1 = nullptr, e_chan1 = nullptr, e_fork = nullptr, e_am = nullptr,
-              e_lin = nullptr, e_fm = nullptr, e_comp_done[2] = {nullptr, nullptr}, e_fetched = nullptr;
+              e_lin = nullptr, e_fm = nullptr, e_comp_done[2] = {nullptr, nullptr}, e_fetched[2] = {nullptr, nullptr};
   int comp_parity = 0;
   int last_nblocks = 0;
   // NCCL (dlopen'ed)
@@ -329,7 +329,7 @@ int ka9q_stream_commit(ka9q_stream* s) {
   K9_CUDA(cudaStreamCreateWithFlags(&s->s_am, cudaStreamNonBlocking));
   K9_CUDA(cudaStreamCreateWithFlags(&s->s_lin, cudaStreamNonBlocking));
   cudaEvent_t* evs[] = {&s->e_pushed, &s->e_fork, &s->e_am, &s->e_lin, &s->e_fm, &s->e_comp_done[0], &s->e_comp_done[1],
-                        &s->e_fetched};
+                        &s->e_fetched[0], &s->e_fetched[1]};
   for (auto e : evs) K9_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   K9_CUDA(cudaEventCreate(&s->e_fft0));
   K9_CUDA(cudaEventCreate(&s->e_fft1));
@@ -353,8 +353,9 @@ int ka9q_stream_commit(ka9q_stream* s) {
   K9_CUDA(cudaMalloc(&s->d_resp, sizeof(float2) * (size_t)K * NDEC));
   K9_CUDA(cudaMalloc(&s->d_params, sizeof(ChanParams) * K));
   K9_CUDA(cudaMalloc(&s->d_state, sizeof(ChanState) * K));
-  K9_CUDA(cudaMalloc(&s->d_status, sizeof(ChanStatus) * (size_t)B * K));
-  K9_CUDA(cudaMemset(s->d_status, 0, sizeof(ChanStatus) * (size_t)B * K));
+  // PCM and status are double-buffered so the D2H copy of batch k overlaps the compute of batch k+1
+  K9_CUDA(cudaMalloc(&s->d_status, sizeof(ChanStatus) * 2 * (size_t)B * K));
+  K9_CUDA(cudaMemset(s->d_status, 0, sizeof(ChanStatus) * 2 * (size_t)B * K));
 
   // parameter blocks, PCM layout, work lists
   s->h_params.resize(K);
@@ -433,8 +434,8 @@ int ka9q_stream_commit(ka9q_stream* s) {
     K9_CUDA(cudaMalloc(&s->d_audio_hist, sizeof(float) * (size_t)K * NDEC));
     K9_CUDA(cudaMemset(s->d_audio_hist, 0, sizeof(float) * (size_t)K * NDEC));  // zero history (filter.c:87)
   }
-  K9_CUDA(cudaMalloc(&s->d_pcm, sizeof(int16_t) * (size_t)B * s->pcm_stride));
-  K9_CUDA(cudaMemset(s->d_pcm, 0, sizeof(int16_t) * (size_t)B * s->pcm_stride));
+  K9_CUDA(cudaMalloc(&s->d_pcm, sizeof(int16_t) * 2 * (size_t)B * s->pcm_stride));
+  K9_CUDA(cudaMemset(s->d_pcm, 0, sizeof(int16_t) * 2 * (size_t)B * s->pcm_stride));
   if (s->cfg.capture_filter_output) K9_CUDA(cudaMalloc(&s->d_filt, sizeof(float2) * (size_t)B * K * s->olen));
   // pinned staging
   K9_CUDA(cudaHostAlloc(&s->h_iq, (size_t)B * L * s->bytes_per_samp, cudaHostAllocDefault));
@@ -529,9 +530,10 @@ static void fill_launch(ka9q_stream* s, ChanLaunch& a, int nblocks) {
   a.resp = s->d_resp;
   a.audio_resp = s->d_audio_resp;
   a.audio_hist = s->d_audio_hist;
-  a.pcm = s->d_pcm;
+  const int wbuf = s->comp_parity ^ 1;  // the buffer this batch writes; fetch reads it once the batch is recorded
+  a.pcm = s->d_pcm + (size_t)wbuf * s->cfg.max_blocks * s->pcm_stride;
   a.pcm_stride = s->pcm_stride;
-  a.status = s->d_status;
+  a.status = s->d_status + (size_t)wbuf * s->cfg.max_blocks * s->chans.size();
   a.nchan_total = (int)s->chans.size();
   a.filt_dbg = s->d_filt;
 }
@@ -613,7 +615,7 @@ static int compute_impl(ka9q_stream* s, int nblocks, bool resident, bool do_fft,
     K9_CHECK((first_block + nblocks) * (long long)s->cfg.L <= s->pushed, "compute ahead of pushed samples");
   }
   K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_pushed, 0));
-  K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_fetched, 0));  // previous results must have left d_pcm
+  K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_fetched[s->comp_parity ^ 1], 0));  // that buffer's results have left
   if (do_fft && issue_fft(s, nblocks, first_block)) return -1;
   if (do_chan && issue_channels(s, nblocks)) return -1;
   if (do_chan || !do_fft) {
@@ -639,12 +641,22 @@ int ka9q_stream_fetch(ka9q_stream* s, int nblocks, int16_t* pcm, ka9q_chan_statu
   K9_CUDA(cudaSetDevice(s->cfg.device));
   K9_CUDA(cudaStreamWaitEvent(s->s_out, s->e_comp_done[s->comp_parity], 0));
   if (pcm)
-    K9_CUDA(cudaMemcpyAsync(pcm, s->d_pcm, sizeof(int16_t) * (size_t)nblocks * s->pcm_stride, cudaMemcpyDeviceToHost,
+    K9_CUDA(cudaMemcpyAsync(pcm, s->d_pcm + (size_t)s->comp_parity * s->cfg.max_blocks * s->pcm_stride,
+                            sizeof(int16_t) * (size_t)nblocks * s->pcm_stride, cudaMemcpyDeviceToHost,
                             s->s_out));
   if (status)
-    K9_CUDA(cudaMemcpyAsync(status, s->d_status, sizeof(ChanStatus) * (size_t)nblocks * s->chans.size(),
+    K9_CUDA(cudaMemcpyAsync(status, s->d_status + (size_t)s->comp_parity * s->cfg.max_blocks * s->chans.size(),
+                            sizeof(ChanStatus) * (size_t)nblocks * s->chans.size(),
                             cudaMemcpyDeviceToHost, s->s_out));
-  K9_CUDA(cudaEventRecord(s->e_fetched, s->s_out));
+  K9_CUDA(cudaEventRecord(s->e_fetched[s->comp_parity], s->s_out));
+  return 0;
+}
+
+// Wait only for the D2H copies issued by ka9q_stream_fetch so far (the compute of the next batch keeps running).
+int ka9q_stream_wait_fetch(ka9q_stream* s) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  K9_CUDA(cudaStreamSynchronize(s->s_out));
   return 0;
 }
 
@@ -738,7 +750,7 @@ int ka9q_stream_destroy(ka9q_stream* s) {
   for (auto st : sts)
     if (st) cudaStreamDestroy(st);
   cudaEvent_t evs[] = {s->e_pushed, s->e_fft0, s->e_fft1, s->e_chan1, s->e_fork, s->e_am, s->e_lin, s->e_fm,
-                       s->e_comp_done[0], s->e_comp_done[1], s->e_fetched};
+                       s->e_comp_done[0], s->e_comp_done[1], s->e_fetched[0], s->e_fetched[1]};
   for (auto e : evs)
     if (e) cudaEventDestroy(e);
   delete s;
