@@ -275,12 +275,9 @@ def run_ours(args, plan):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        # nvidia-smi needs ~0.2 s to come up: keep the GPU under the same load until it samples, then time
-        t_end = time.perf_counter() + 0.4
-        while time.perf_counter() < t_end:
-            step_resident()
-            c.sync()
-    for _ in range(args.warmup):
+    # nvidia-smi needs a few hundred ms to come up: every rank runs the same fixed number of extra untimed steps (the
+    # multi-GPU step contains a collective, so the count must not depend on the rank or on wall time)
+    for _ in range(args.warmup + 300):
         step_resident()
     barrier()
     c.timer_start()
