@@ -207,6 +207,9 @@ def run_ours(args, plan):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B = args.blocks
+    if multi and args.mgpu == "allgather":
+        B = max(B, world)
+        B += (-B) % world          # the block-sharded forward FFT needs blocks_per_step % n_gpus == 0
     c = ch.Channelizer(plan.samprate, plan.L, plan.M, plan.D, device=local, max_blocks=B)
     for spec in plan.channels:
         c.add_channel(spec.mode, spec.bin, low=spec.low, high=spec.high)
@@ -216,8 +219,8 @@ def run_ours(args, plan):
     # synthetic input (rank 0 ingests the stream); pinned host buffers for the end-to-end leg
     nbytes_in = B * plan.L * 4
     pin_in = ch.PinnedBuffer(nbytes_in, np.int16)
-    if rank == 0:
-        pin_in.array[:] = make_input(plan, B)
+    if rank == 0 or args.mgpu == "allgather":
+        pin_in.array[:] = make_input(plan, B)   # block-sharded FFT: every rank ingests the (int16) stream
     pin_pcm = [ch.PinnedBuffer(B * c.pcm_stride * 2, np.int16) for _ in range(2)]
     in_ptr = C.c_void_p(pin_in.ptr)
     pcm_ptrs = [C.c_void_p(p.ptr) for p in pin_pcm]
@@ -235,13 +238,24 @@ def run_ours(args, plan):
         torch.cuda.synchronize()
         c.sync()
 
-    def step_resident():
-        if not multi:
-            c.compute_resident(B)
+    def spectrum_step():
+        """Multi-GPU: produce the batch's spectra on every rank. `allgather` (default): rank r transforms blocks
+        [r*B/G, (r+1)*B/G) and the spectra are all-gathered (forward FFT sharded by block, every rank ingests the int16
+        stream); `broadcast`: rank 0 transforms everything and broadcasts. Both run on the library's FFT stream and
+        overlap the channel kernels of the previous batch."""
+        if args.mgpu == "allgather":
+            c.compute_fft_blocks(B, rank * (B // world), B // world)
+            c.nccl_allgather_spectrum(B)
         else:
             if rank == 0:
                 c.compute_fft_only(B)
             c.nccl_broadcast_spectrum(B, 0)
+
+    def step_resident():
+        if not multi:
+            c.compute_resident(B)
+        else:
+            spectrum_step()
             c.compute_channels_only(B)
 
     e2e_count = [0]
@@ -253,15 +267,13 @@ def run_ours(args, plan):
         previous batch's copy-out (wait_fetch) before re-using that host buffer."""
         i = e2e_count[0]
         e2e_count[0] += 1
-        if not multi or rank == 0:
+        if not multi or rank == 0 or args.mgpu == "allgather":
             c.push(in_ptr, B)
         if not multi:
             c.compute(B)
         else:
-            # the stream enters the box once (rank 0); every rank returns its own PCM rows to the host
-            if rank == 0:
-                c.compute_fft_only(B)
-            c.nccl_broadcast_spectrum(B, 0)
+            # every rank returns its own PCM rows to the host
+            spectrum_step()
             c.compute_channels_only(B)
         c.wait_fetch()                 # batch i-1 has landed in host memory
         c.fetch(B, pcm_ptrs[i & 1])    # batch i: queued behind its compute, overlaps the next batch
@@ -308,7 +320,7 @@ def run_ours(args, plan):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = world * K * (B * plan.L / 1e6) / e2e_s
-    h2d = nbytes_in if True else 0
+    h2d = nbytes_in * (world if (multi and args.mgpu == "allgather") else 1)
     d2h = world * B * c.pcm_stride * 2
 
     if rank != 0:
@@ -366,7 +378,9 @@ def run_ours(args, plan):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": plan.name, "channels_per_gpu": K, "samprate": plan.samprate, "L": plan.L, "M": plan.M,
                    "N": plan.N, "decimate": plan.D, "blocks_per_step": B, "block_ms": 20,
-                   "parallelism": "1 GPU" if not multi else f"channels x{world} (weak), NCCL spectrum broadcast from rank 0",
+                   "parallelism": "1 GPU" if not multi else (
+                       f"channels x{world} (weak); forward FFT sharded by block + NCCL all-gather of spectra"
+                       if args.mgpu == "allgather" else f"channels x{world} (weak); NCCL spectrum broadcast from rank 0"),
                    "l2": f"per-step working set {work_mb:.0f} MB > 126 MB L2 (responses+state+spectra+PCM); no flush needed"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -396,6 +410,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--ref-blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mgpu", default="allgather", choices=["allgather", "broadcast"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     plan = make_plan(args.config, args.channels)

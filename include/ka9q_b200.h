@@ -257,10 +257,14 @@ int ka9q_stream_timer_stop(ka9q_stream *s, float *ms_total, float *class_ms, int
 int ka9q_stream_spectrum_ptr(ka9q_stream *s, void **dev_ptr, long long *bytes_per_block);
 int ka9q_stream_compute_fft_only(ka9q_stream *s, int nblocks);
 int ka9q_stream_compute_channels_only(ka9q_stream *s, int nblocks);
+/* forward FFT of blocks [first, first+count) of the resident batch only (FFT sharded by block across ranks) */
+int ka9q_stream_compute_fft_blocks(ka9q_stream *s, int nblocks, int first, int count);
 /* NCCL spectrum broadcast inside the library (libnccl.so.2 is dlopen'ed on first use). */
 int ka9q_nccl_unique_id(void *id128);
 int ka9q_stream_nccl_init(ka9q_stream *s, const void *id128, int rank, int nranks);
 int ka9q_stream_nccl_broadcast_spectrum(ka9q_stream *s, int nblocks, int root);
+/* every rank transformed its nblocks/nranks blocks (compute_fft_blocks); gather all nblocks spectra on every rank */
+int ka9q_stream_nccl_allgather_spectrum(ka9q_stream *s, int nblocks);
 
 /* Introspection for parity tests (device -> host copies, synchronous). */
 int ka9q_stream_get_response(ka9q_stream *s, int chan, KA9Q_CFLOAT *out2048, float *noise_gain);

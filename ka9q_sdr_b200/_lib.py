@@ -61,7 +61,8 @@ EXPORTED = [
     "ka9q_nccl_unique_id", "ka9q_stream_nccl_init", "ka9q_stream_nccl_broadcast_spectrum", "ka9q_stream_get_response",
     "ka9q_stream_get_filter_output", "ka9q_stream_get_spectrum", "ka9q_stream_get_if_energy", "ka9q_fft_c2c",
     "ka9q_fft_plan_describe", "ka9q_hb15_cascade", "ka9q_host_alloc", "ka9q_host_free", "ka9q_stream_timer_start",
-    "ka9q_stream_timer_stop", "ka9q_osc_run", "ka9q_stream_wait_fetch",
+    "ka9q_stream_timer_stop", "ka9q_osc_run", "ka9q_stream_wait_fetch", "ka9q_stream_compute_fft_blocks",
+    "ka9q_stream_nccl_allgather_spectrum",
 ]
 
 
@@ -97,6 +98,8 @@ def lib():
     L.ka9q_stream_compute_channels_only.argtypes = [vp, ci]
     L.ka9q_stream_fetch.argtypes = [vp, ci, vp, vp]
     L.ka9q_stream_sync.argtypes = [vp]
+    L.ka9q_stream_compute_fft_blocks.argtypes = [vp, ci, ci, ci]
+    L.ka9q_stream_nccl_allgather_spectrum.argtypes = [vp, ci]
     L.ka9q_stream_wait_fetch.argtypes = [vp]
     L.ka9q_stream_last_timing.argtypes = [vp, C.POINTER(cf), C.POINTER(cf), C.POINTER(cf)]
     L.ka9q_stream_spectrum_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(cll)]

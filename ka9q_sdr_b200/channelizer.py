@@ -182,6 +182,12 @@ class Channelizer:
         buf = C.create_string_buffer(id128, 128)
         _lib.check(self.lib.ka9q_stream_nccl_init(self.h, buf, rank, nranks), "nccl_init")
 
+    def compute_fft_blocks(self, nblocks: int, first: int, count: int):
+        _lib.check(self.lib.ka9q_stream_compute_fft_blocks(self.h, nblocks, first, count), "compute_fft_blocks")
+
+    def nccl_allgather_spectrum(self, nblocks: int):
+        _lib.check(self.lib.ka9q_stream_nccl_allgather_spectrum(self.h, nblocks), "nccl_allgather_spectrum")
+
     def nccl_broadcast_spectrum(self, nblocks: int, root: int = 0):
         _lib.check(self.lib.ka9q_stream_nccl_broadcast_spectrum(self.h, nblocks, root), "nccl_broadcast_spectrum")
 

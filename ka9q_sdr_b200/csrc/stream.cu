@@ -81,8 +81,13 @@ struct ka9q_stream {
               e_lin = nullptr, e_fm = nullptr, e_comp_done[2] = {nullptr, nullptr}, e_fetched[2] = {nullptr, nullptr};
   int comp_parity = 0;
   int last_nblocks = 0;
+  cudaStream_t s_fft = nullptr;
+  cudaEvent_t e_spec_ready[2] = {nullptr, nullptr}, e_spec_free[2] = {nullptr, nullptr};
+  int spec_wr = 0, spec_rd = 0, spec_published = 0;
+  bool fft_pending = false;
   // NCCL (dlopen'ed)
   void* nccl_comm = nullptr;
+  int nccl_rank = 0, nccl_nranks = 1;
   // live timing of the timed region (bench.py): event pairs around every forward FFT and every FM/AM/linear launch
   bool timing = false;
   cudaEvent_t e_t0 = nullptr, e_t1 = nullptr;
@@ -328,8 +333,10 @@ int ka9q_stream_commit(ka9q_stream* s) {
   K9_CUDA(cudaStreamCreateWithFlags(&s->s_fm, cudaStreamNonBlocking));
   K9_CUDA(cudaStreamCreateWithFlags(&s->s_am, cudaStreamNonBlocking));
   K9_CUDA(cudaStreamCreateWithFlags(&s->s_lin, cudaStreamNonBlocking));
+  K9_CUDA(cudaStreamCreateWithFlags(&s->s_fft, cudaStreamNonBlocking));
   cudaEvent_t* evs[] = {&s->e_pushed, &s->e_fork, &s->e_am, &s->e_lin, &s->e_fm, &s->e_comp_done[0], &s->e_comp_done[1],
-                        &s->e_fetched[0], &s->e_fetched[1]};
+                        &s->e_fetched[0], &s->e_fetched[1], &s->e_spec_ready[0], &s->e_spec_ready[1], &s->e_spec_free[0],
+                        &s->e_spec_free[1]};
   for (auto e : evs) K9_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   K9_CUDA(cudaEventCreate(&s->e_fft0));
   K9_CUDA(cudaEventCreate(&s->e_fft1));
@@ -339,7 +346,7 @@ int ka9q_stream_commit(ka9q_stream* s) {
   s->ring_cap = (long long)(M - 1) + 2LL * B * L;
   K9_CUDA(cudaMalloc(&s->d_ring, (size_t)s->ring_cap * s->bytes_per_samp));
   K9_CUDA(cudaMemset(s->d_ring, 0, (size_t)s->ring_cap * s->bytes_per_samp));  // zero history (filter.c:77)
-  K9_CUDA(cudaMalloc(&s->d_spec, sizeof(float2) * (size_t)B * N));
+  K9_CUDA(cudaMalloc(&s->d_spec, sizeof(float2) * 2 * (size_t)B * N));  // double-buffered (see issue_fft)
   K9_CUDA(cudaMalloc(&s->d_tmp0, sizeof(float2) * (size_t)B * N));
   if (s->fwd.npass >= 3) K9_CUDA(cudaMalloc(&s->d_tmp1, sizeof(float2) * (size_t)B * N));
   K9_CUDA(cudaMalloc(&s->d_energy, sizeof(float) * B));
@@ -538,33 +545,61 @@ static void fill_launch(ka9q_stream* s, ChanLaunch& a, int nblocks) {
   a.filt_dbg = s->d_filt;
 }
 
-static int issue_fft(ka9q_stream* s, int nblocks, long long first_block) {
+// The spectrum is double-buffered and the forward FFT (+ the multi-GPU collective) runs on its own stream, so the FFT
+// of batch k+1 overlaps the channel kernels of batch k:
+//   s_fft : [wait ring pushed, buffer p free] FFT -> (collective) -> record ready[p]
+//   s_comp: [wait ready[p]] channel kernels -> record free[p]
+static float2* spec_buf(ka9q_stream* s, int p) { return s->d_spec + (size_t)p * s->cfg.max_blocks * s->N; }
+
+static int issue_fft(ka9q_stream* s, long long first_block, int blk_first, int blk_count) {
+  const int p = s->spec_wr;
+  K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_pushed, 0));
+  K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_spec_free[p], 0));
+  if (blk_count <= 0) return 0;
   BigFftIn in;
   in.in_mode = s->cfg.iq_format == KA9Q_IQ_S16 ? IN_RING_S16 : IN_RING_S8;
   in.in = s->d_ring;
   in.ring_cap = s->ring_cap;
-  in.ring_off = (first_block * (long long)s->cfg.L) % s->ring_cap;
+  in.ring_off = ((first_block + blk_first) * (long long)s->cfg.L) % s->ring_cap;
   in.ring_step = s->cfg.L;
   in.scale = s->cfg.iq_format == KA9Q_IQ_S16 ? (float)(1. / 32767) : (float)(1. / 127);  // radio.c:38-39
   in.gain = s->cfg.gain_factor;
   in.stat_from = s->cfg.M - 1;
-  in.energy = s->d_energy;
-  K9_CUDA(cudaMemsetAsync(s->d_energy, 0, sizeof(float) * nblocks, s->s_comp));
-  K9_CUDA(cudaEventRecord(s->e_fft0, s->s_comp));
+  in.energy = s->d_energy + blk_first;
+  K9_CUDA(cudaMemsetAsync(s->d_energy + blk_first, 0, sizeof(float) * blk_count, s->s_fft));
+  K9_CUDA(cudaEventRecord(s->e_fft0, s->s_fft));
   {
-    TimedRegion tr(s, TC_FFT, s->s_comp);
-    if (bigfft_exec(&s->fwd, in, s->d_spec, s->N, s->d_tmp0, s->d_tmp1, nblocks, -1, s->s_comp)) {
+    TimedRegion tr(s, TC_FFT, s->s_fft);
+    if (bigfft_exec(&s->fwd, in, spec_buf(s, p) + (size_t)blk_first * s->N, s->N, s->d_tmp0, s->d_tmp1, blk_count, -1,
+                    s->s_fft)) {
       set_error("forward FFT launch failed");
       return -1;
     }
   }
-  K9_CUDA(cudaEventRecord(s->e_fft1, s->s_comp));
+  K9_CUDA(cudaEventRecord(s->e_fft1, s->s_fft));
+  s->fft_pending = true;
+  return 0;
+}
+
+// the spectrum buffer being written is complete (FFT and, on multi-GPU runs, the collective): hand it to the channels
+static int publish_spectrum(ka9q_stream* s) {
+  K9_CUDA(cudaEventRecord(s->e_spec_ready[s->spec_wr], s->s_fft));
+  s->spec_wr ^= 1;
+  s->spec_published++;
+  s->fft_pending = false;
   return 0;
 }
 
 static int issue_channels(ka9q_stream* s, int nblocks) {
+  if (s->fft_pending && publish_spectrum(s)) return -1;
+  K9_CHECK(s->spec_published > 0, "no spectrum has been computed or received for this batch");
+  s->spec_published--;
+  const int p = s->spec_rd;
+  K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_spec_ready[p], 0));
+  K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_fetched[s->comp_parity ^ 1], 0));  // that PCM buffer's results have left
   ChanLaunch a;
   fill_launch(s, a, nblocks);
+  a.spec = spec_buf(s, p);
   // the three demodulator families run concurrently on sibling streams
   K9_CUDA(cudaEventRecord(s->e_fork, s->s_comp));
   if (s->n_am) {
@@ -596,43 +631,56 @@ static int issue_channels(ka9q_stream* s, int nblocks) {
   if (s->n_am) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_am, 0));
   if (s->n_lin) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_lin, 0));
   K9_CUDA(cudaEventRecord(s->e_chan1, s->s_comp));
+  K9_CUDA(cudaEventRecord(s->e_spec_free[p], s->s_comp));
+  s->spec_rd ^= 1;
   s->phase_block += nblocks;
+  s->comp_parity ^= 1;
+  K9_CUDA(cudaEventRecord(s->e_comp_done[s->comp_parity], s->s_comp));
+  s->last_nblocks = nblocks;
   return 0;
 }
 
-static int compute_impl(ka9q_stream* s, int nblocks, bool resident, bool do_fft, bool do_chan) {
+// which blocks of the ring a batch covers: streaming mode consumes the next unprocessed blocks, resident mode re-runs
+// the most recently pushed ones (benchmarks with the input already in HBM)
+static int batch_first_block(ka9q_stream* s, int nblocks, bool resident, long long* first_block) {
   K9_CHECK(s && s->committed, "stream not committed");
   K9_CHECK(nblocks >= 1 && nblocks <= s->cfg.max_blocks, "nblocks out of range");
   K9_CUDA(cudaSetDevice(s->cfg.device));
-  long long first_block;
   if (resident) {
-    first_block = s->pushed / s->cfg.L - nblocks;
-    K9_CHECK(first_block >= 0, "not enough samples resident in the ring");
-    // resident re-runs keep the true block index for the ring window but a running index for LO phase/audio ring
-    if (s->phase_block < first_block) s->phase_block = first_block;
+    *first_block = s->pushed / s->cfg.L - nblocks;
+    K9_CHECK(*first_block >= 0, "not enough samples resident in the ring");
+    if (s->phase_block < *first_block) s->phase_block = *first_block;
   } else {
-    first_block = s->block0;
-    K9_CHECK((first_block + nblocks) * (long long)s->cfg.L <= s->pushed, "compute ahead of pushed samples");
+    *first_block = s->block0;
+    K9_CHECK((*first_block + nblocks) * (long long)s->cfg.L <= s->pushed, "compute ahead of pushed samples");
   }
-  K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_pushed, 0));
-  K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_fetched[s->comp_parity ^ 1], 0));  // that buffer's results have left
-  if (do_fft && issue_fft(s, nblocks, first_block)) return -1;
+  return 0;
+}
+
+static int compute_impl(ka9q_stream* s, int nblocks, bool resident, bool do_fft, bool do_chan, int blk_first = 0,
+                        int blk_count = -1) {
+  long long first_block = 0;
+  if (batch_first_block(s, nblocks, resident, &first_block)) return -1;
+  if (blk_count < 0) blk_count = nblocks - blk_first;
+  K9_CHECK(blk_first >= 0 && blk_first + blk_count <= nblocks, "block range out of the batch");
+  if (do_fft && issue_fft(s, first_block, blk_first, blk_count)) return -1;
+  if (do_fft && do_chan && publish_spectrum(s)) return -1;
   if (do_chan && issue_channels(s, nblocks)) return -1;
-  if (do_chan || !do_fft) {
-    s->comp_parity ^= 1;
-    K9_CUDA(cudaEventRecord(s->e_comp_done[s->comp_parity], s->s_comp));
-    s->last_nblocks = nblocks;
+  if (do_fft || !resident) {
+    if (resident)
+      s->block0 = s->pushed / s->cfg.L;  // everything pushed so far counts as consumed
+    else if (do_chan || !do_fft)
+      s->block0 += nblocks;
   }
-  if (resident)
-    s->block0 = s->pushed / s->cfg.L;  // everything pushed so far counts as consumed
-  else
-    s->block0 += nblocks;
   return 0;
 }
 
 int ka9q_stream_compute(ka9q_stream* s, int nblocks) { return compute_impl(s, nblocks, false, true, true); }
 int ka9q_stream_compute_resident(ka9q_stream* s, int nblocks) { return compute_impl(s, nblocks, true, true, true); }
 int ka9q_stream_compute_fft_only(ka9q_stream* s, int nblocks) { return compute_impl(s, nblocks, true, true, false); }
+int ka9q_stream_compute_fft_blocks(ka9q_stream* s, int nblocks, int first, int count) {
+  return compute_impl(s, nblocks, true, true, false, first, count);
+}
 int ka9q_stream_compute_channels_only(ka9q_stream* s, int nblocks) { return compute_impl(s, nblocks, true, false, true); }
 
 int ka9q_stream_fetch(ka9q_stream* s, int nblocks, int16_t* pcm, ka9q_chan_status* status) {
@@ -664,6 +712,7 @@ int ka9q_stream_sync(ka9q_stream* s) {
   K9_CHECK(s && s->committed, "stream not committed");
   K9_CUDA(cudaSetDevice(s->cfg.device));
   K9_CUDA(cudaStreamSynchronize(s->s_in));
+  K9_CUDA(cudaStreamSynchronize(s->s_fft));
   K9_CUDA(cudaStreamSynchronize(s->s_comp));
   K9_CUDA(cudaStreamSynchronize(s->s_am));
   K9_CUDA(cudaStreamSynchronize(s->s_lin));
@@ -692,7 +741,7 @@ int ka9q_stream_last_timing(ka9q_stream* s, float* total_ms, float* fft_ms, floa
 
 int ka9q_stream_spectrum_ptr(ka9q_stream* s, void** dev_ptr, long long* bytes_per_block) {
   K9_CHECK(s && s->committed, "stream not committed");
-  if (dev_ptr) *dev_ptr = s->d_spec;
+  if (dev_ptr) *dev_ptr = spec_buf(s, s->spec_rd ^ 1);  // the buffer the last channel launch read
   if (bytes_per_block) *bytes_per_block = (long long)sizeof(float2) * s->N;
   return 0;
 }
@@ -721,7 +770,8 @@ int ka9q_stream_get_spectrum(ka9q_stream* s, int block, void* outN) {
   K9_CHECK(s && s->committed, "stream not committed");
   K9_CHECK(block >= 0 && block < s->cfg.max_blocks, "bad block");
   K9_CUDA(cudaSetDevice(s->cfg.device));
-  K9_CUDA(cudaMemcpy(outN, s->d_spec + (size_t)block * s->N, sizeof(float2) * s->N, cudaMemcpyDeviceToHost));
+  K9_CUDA(cudaStreamSynchronize(s->s_fft));
+  K9_CUDA(cudaMemcpy(outN, spec_buf(s, s->spec_rd ^ 1) + (size_t)block * s->N, sizeof(float2) * s->N, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -829,6 +879,7 @@ static int (*p_ncclGetUniqueId)(k9_ncclUniqueId*);
 static int (*p_ncclCommInitRank)(k9_ncclComm_t*, int, k9_ncclUniqueId, int);
 static int (*p_ncclBroadcast)(const void*, void*, size_t, int, int, k9_ncclComm_t, cudaStream_t);
 static int (*p_ncclCommDestroy)(k9_ncclComm_t);
+static int (*p_ncclAllGather)(const void*, void*, size_t, int, k9_ncclComm_t, cudaStream_t);
 static const char* (*p_ncclGetErrorString)(int);
 
 static int load_nccl() {
@@ -845,6 +896,7 @@ static int load_nccl() {
   p_ncclCommInitRank = (int (*)(k9_ncclComm_t*, int, k9_ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
   p_ncclBroadcast = (int (*)(const void*, void*, size_t, int, int, k9_ncclComm_t, cudaStream_t))dlsym(h, "ncclBroadcast");
   p_ncclCommDestroy = (int (*)(k9_ncclComm_t))dlsym(h, "ncclCommDestroy");
+  p_ncclAllGather = (int (*)(const void*, void*, size_t, int, k9_ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
   p_ncclGetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
   if (!p_ncclGetUniqueId || !p_ncclCommInitRank || !p_ncclBroadcast) {
     state = -1;
@@ -875,22 +927,48 @@ int ka9q_stream_nccl_init(ka9q_stream* s, const void* id128, int rank, int nrank
   int r = p_ncclCommInitRank(&comm, nranks, id, rank);
   K9_CHECK(r == 0, "ncclCommInitRank: %s", p_ncclGetErrorString ? p_ncclGetErrorString(r) : "error");
   s->nccl_comm = comm;
+  s->nccl_rank = rank;
+  s->nccl_nranks = nranks;
   return 0;
 }
 
+// Both collectives run on the FFT stream right behind the forward transform(s) of the batch being written and then
+// publish that spectrum buffer to the channel kernels, so they overlap the channel work of the previous batch.
 int ka9q_stream_nccl_broadcast_spectrum(ka9q_stream* s, int nblocks, int root) {
   K9_CHECK(s && s->committed && s->nccl_comm, "NCCL communicator not initialised");
   K9_CHECK(nblocks >= 1 && nblocks <= s->cfg.max_blocks, "nblocks out of range");
   K9_CUDA(cudaSetDevice(s->cfg.device));
-  // float32 count: 2 floats per bin; ordered on the compute stream right after the forward FFT
-  const size_t count = (size_t)2 * s->N * nblocks;
+  K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_spec_free[s->spec_wr], 0));
+  float2* buf = spec_buf(s, s->spec_wr);
+  const size_t count = (size_t)2 * s->N * nblocks;  // float32 count: 2 floats per bin
   int r;
   {
-    TimedRegion tr(s, TC_BCAST, s->s_comp);
-    r = p_ncclBroadcast(s->d_spec, s->d_spec, count, /*ncclFloat32=*/7, root, (k9_ncclComm_t)s->nccl_comm, s->s_comp);
+    TimedRegion tr(s, TC_BCAST, s->s_fft);
+    r = p_ncclBroadcast(buf, buf, count, /*ncclFloat32=*/7, root, (k9_ncclComm_t)s->nccl_comm, s->s_fft);
   }
   K9_CHECK(r == 0, "ncclBroadcast: %s", p_ncclGetErrorString ? p_ncclGetErrorString(r) : "error");
-  return 0;
+  return publish_spectrum(s);
+}
+
+// Forward FFT sharded by block: rank r transformed blocks [r*nblocks/nranks, (r+1)*nblocks/nranks) of the batch
+// (ka9q_stream_compute_fft_blocks; every rank holds the int16 input, which is 4x smaller than the spectrum); the
+// all-gather completes every rank's copy of all nblocks spectra. nblocks must be a multiple of nranks.
+int ka9q_stream_nccl_allgather_spectrum(ka9q_stream* s, int nblocks) {
+  K9_CHECK(s && s->committed && s->nccl_comm && p_ncclAllGather, "NCCL communicator not initialised");
+  K9_CHECK(nblocks >= 1 && nblocks <= s->cfg.max_blocks && nblocks % s->nccl_nranks == 0,
+           "nblocks must be a multiple of the number of ranks");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_spec_free[s->spec_wr], 0));
+  float2* buf = spec_buf(s, s->spec_wr);
+  const size_t per_rank = (size_t)2 * s->N * (nblocks / s->nccl_nranks);
+  int r;
+  {
+    TimedRegion tr(s, TC_BCAST, s->s_fft);
+    r = p_ncclAllGather((const float*)buf + per_rank * s->nccl_rank, buf, per_rank, /*ncclFloat32=*/7,
+                        (k9_ncclComm_t)s->nccl_comm, s->s_fft);
+  }
+  K9_CHECK(r == 0, "ncclAllGather: %s", p_ncclGetErrorString ? p_ncclGetErrorString(r) : "error");
+  return publish_spectrum(s);
 }
 
 // ------------------------------------------------------------------ generic FFT on host buffers (tests / cross-checks)
