@@ -248,6 +248,8 @@ int ka9q_stream_last_timing(ka9q_stream *s, float *total_ms, float *fft_ms, floa
 /* Timed region for benchmarks: CUDA events on the compute stream around the region, plus one event pair around every
  * forward FFT and every channel-kernel launch inside it. class_ms[5]/class_launches[5] = {forward FFT, FM kernel,
  * AM kernel, linear kernel, NCCL spectrum broadcast}. timer_stop synchronises. */
+/* 1 (default): the forward FFT of batch k+1 overlaps the channel kernels of batch k; 0: serialised (per-kernel timing) */
+int ka9q_stream_set_overlap(ka9q_stream *s, int enable);
 int ka9q_stream_timer_start(ka9q_stream *s);
 int ka9q_stream_timer_stop(ka9q_stream *s, float *ms_total, float *class_ms, int *class_launches);
 

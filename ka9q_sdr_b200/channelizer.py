@@ -166,6 +166,9 @@ class Channelizer:
         _lib.check(self.lib.ka9q_stream_last_timing(self.h, C.byref(t), C.byref(f), C.byref(c)), "last_timing")
         return t.value, f.value, c.value
 
+    def set_overlap(self, enable: bool):
+        _lib.check(self.lib.ka9q_stream_set_overlap(self.h, 1 if enable else 0), "set_overlap")
+
     def timer_start(self):
         _lib.check(self.lib.ka9q_stream_timer_start(self.h), "timer_start")
 

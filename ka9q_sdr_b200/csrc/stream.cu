@@ -85,6 +85,7 @@ struct ka9q_stream {
   cudaEvent_t e_spec_ready[2] = {nullptr, nullptr}, e_spec_free[2] = {nullptr, nullptr};
   int spec_wr = 0, spec_rd = 0, spec_published = 0;
   bool fft_pending = false;
+  bool overlap = true;  // false: the forward FFT waits for the previous batch's channel kernels (per-kernel timing)
   // NCCL (dlopen'ed)
   void* nccl_comm = nullptr;
   int nccl_rank = 0, nccl_nranks = 1;
@@ -555,6 +556,7 @@ static int issue_fft(ka9q_stream* s, long long first_block, int blk_first, int b
   const int p = s->spec_wr;
   K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_pushed, 0));
   K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_spec_free[p], 0));
+  if (!s->overlap) K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_comp_done[s->comp_parity], 0));
   if (blk_count <= 0) return 0;
   BigFftIn in;
   in.in_mode = s->cfg.iq_format == KA9Q_IQ_S16 ? IN_RING_S16 : IN_RING_S8;
@@ -808,6 +810,14 @@ int ka9q_stream_destroy(ka9q_stream* s) {
 }
 
 
+
+// Overlap of the forward FFT (batch k+1) with the channel kernels (batch k) is on by default; switching it off
+// serialises them so that per-kernel event timings are those of each kernel running alone.
+int ka9q_stream_set_overlap(ka9q_stream* s, int enable) {
+  K9_CHECK(s, "null argument");
+  s->overlap = enable != 0;
+  return 0;
+}
 
 // ------------------------------------------------------------------ timed region (bench.py)
 // timer_start/stop bracket a region with CUDA events on the compute stream (the stream every kernel of this library
