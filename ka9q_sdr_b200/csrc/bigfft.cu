@@ -12,32 +12,38 @@ namespace k9 {
 
 // ---------------- device side ----------------
 
-__device__ __forceinline__ float2 load_input(const PassArgs& a, int batch, int idx) {
+// ring position of logical index idx of batch `batch`: base = (ring_off + batch*ring_step) mod cap is reduced once per
+// thread (ring_base), then every element needs a single conditional subtract instead of a 64-bit modulo
+__device__ __forceinline__ long long ring_base(const PassArgs& a, int batch) {
+  return (a.ring_off + (long long)batch * a.ring_step) % a.ring_cap;
+}
+__device__ __forceinline__ long long ring_pos(const PassArgs& a, long long base, int idx) {
+  long long pos = base + idx;  // idx < N <= cap
+  return pos >= a.ring_cap ? pos - a.ring_cap : pos;
+}
+
+__device__ __forceinline__ float2 load_input(const PassArgs& a, int batch, long long base, int idx) {
   switch (a.in_mode) {
     default:
     case IN_C32:
       return reinterpret_cast<const float2*>(a.in)[(long long)batch * a.in_batch_stride + idx];
     case IN_RING_S16: {
-      long long pos = a.ring_off + (long long)batch * a.ring_step + idx;
-      pos %= a.ring_cap;
+      const long long pos = ring_pos(a, base, idx);
       short2 v = reinterpret_cast<const short2*>(a.in)[pos];
       // reference radio.c:113-114,122: (float)int16 * SCALE16, then * gain_factor
       return make_float2(((float)v.x * a.scale) * a.gain, ((float)v.y * a.scale) * a.gain);
     }
     case IN_RING_S8: {
-      long long pos = a.ring_off + (long long)batch * a.ring_step + idx;
-      pos %= a.ring_cap;
+      const long long pos = ring_pos(a, base, idx);
       char2 v = reinterpret_cast<const char2*>(a.in)[pos];
       return make_float2(((float)v.x * a.scale) * a.gain, ((float)v.y * a.scale) * a.gain);
     }
     case IN_RING_C32: {
-      long long pos = a.ring_off + (long long)batch * a.ring_step + idx;
-      pos %= a.ring_cap;
+      const long long pos = ring_pos(a, base, idx);
       return reinterpret_cast<const float2*>(a.in)[pos];
     }
     case IN_RING_R32: {
-      long long pos = a.ring_off + (long long)batch * a.ring_step + idx;
-      pos %= a.ring_cap;
+      const long long pos = ring_pos(a, base, idx);
       return make_float2(reinterpret_cast<const float*>(a.in)[pos], 0.f);
     }
   }
@@ -68,6 +74,7 @@ __global__ void __launch_bounds__(T*(R1 > R2 ? R1 : R2)) fft_pass_kernel(const P
 
   // ---- sub-pass A ----
   float esum = 0.f;
+  const long long rbase = (a.in_mode == IN_C32) ? 0 : ring_base(a, batch);
   if (tid < T * R2) {
     const int col = tid % T;
     const int p = tid / T;
@@ -77,7 +84,7 @@ __global__ void __launch_bounds__(T*(R1 > R2 ? R1 : R2)) fft_pass_kernel(const P
 #pragma unroll
       for (int r = 0; r < R1; r++) {
         const int idx = c + a.ncols * (p + R2 * r);
-        v[r] = load_input(a, batch, idx);
+        v[r] = load_input(a, batch, rbase, idx);
         if (a.energy != nullptr && idx >= a.stat_from) esum += v[r].x * v[r].x + v[r].y * v[r].y;
       }
       Dft<R1, SIGN>::run(v);
