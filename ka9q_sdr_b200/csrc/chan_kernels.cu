@@ -147,7 +147,7 @@ __device__ __forceinline__ int phase_advance(int e, int step, int N) {
   return e >= N ? e - N : e;
 }
 
-// After the inverse transform (output already in buf, natural order): this thread's partial sums of |y|^2 and |y| and
+// (generic variant, reading back from the buffer) After the inverse transform: this thread's partial sums of |y|^2 and |y| and
 // its minimum |y|^2 over the kept samples n in [first, NDEC). Each thread reads only the elements it stored itself
 // (n = t + 128j), so no barrier is needed between store16 and this. The per-block LO phase (Appendix C) is NOT applied
 // here: |y| does not depend on it; the consumers that do (discriminator state across blocks, linear output, the debug
@@ -164,6 +164,31 @@ __device__ __forceinline__ void kept_stats(const float2* __restrict__ buf, int f
       mn = fminf(mn, q);
       // |y| for the squelch statistics only (fm.c:95): MUFU.RSQ based, ~1 ulp; it only feeds threshold decisions
       samp += (q > 0.f) ? q * rsqrtf(q) : 0.f;
+    }
+  }
+  *sumsq = ssq;
+  *sumamp = samp;
+  *minsq = mn;
+}
+
+// store16 + kept_stats in one pass over the registers (rows j >= jb only; the row j == jb is partly history)
+__device__ __forceinline__ void store16_stats(const float2 (&v)[16], float2* __restrict__ buf, int first, float* sumsq,
+                                              float* sumamp, float* minsq) {
+  const int t = threadIdx.x;
+  const int jb = first >> 7, rem = first & 127;
+  float2* bp = buf + t;
+  float ssq = 0.f, samp = 0.f, mn = INFINITY;
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    if (j >= jb) {  // warp-uniform
+      bp[128 * j] = v[j];
+      float q = v[j].x * v[j].x + v[j].y * v[j].y;
+      const bool kept = (j > jb) || (t >= rem);
+      ssq += kept ? q : 0.f;
+      mn = fminf(mn, kept ? q : INFINITY);
+      // |y| for the squelch statistics only (fm.c:95): MUFU.RSQ based, ~1 ulp; it only feeds threshold decisions
+      q = fmaxf(q, 1e-37f);
+      samp += kept ? q * rsqrtf(q) : 0.f;
     }
   }
   *sumsq = ssq;
@@ -250,12 +275,14 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
   }
   const bool open = below < 2;
   float2 new_state = make_float2(0.f, 0.f);
+  float dbg_allgood = -1.f;
   float new_last = 0.f, foffset = sh.S[h].fm_foffset, pdeviation = sh.S[h].fm_pdeviation;
   if (open) {
     const float min_ampl = 0.55f * 0.55f * avg_amp * avg_amp;  // fm.c:121
     const float2 old_state = cmul(sh.S[h].fm_state, ph);       // into this block's unrotated domain
     const float old_last = sh.S[h].fm_lastaudio;
     const bool all_good = minsq > min_ampl;  // every sample passes the blanking threshold (the usual case)
+    dbg_allgood = all_good ? 1.f : 0.f;
     if (!all_good) {
       // good-sample bitmap, one ballot per 32 samples
 #pragma unroll 2
@@ -272,47 +299,70 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
       __syncthreads();
     }
     float fsum = 0.f, pos = -INFINITY, neg = INFINITY;
-    const int lane = t & 31;
-#pragma unroll 2
-    for (int i = 0; i < 8; i++) {
-      const int o = t + 128 * i;
-      if (o < olen) {
-        bool g = true, gp = true;
-        if (!all_good) {
-          const unsigned wbits = sh.good[o >> 5];
-          g = (wbits >> lane) & 1u;
-          gp = lane ? ((wbits >> (lane - 1)) & 1u) : (o ? (sh.good[(o >> 5) - 1] >> 31) : 1u);
-        }
-        // audio[n] = arg(y[src] * conj(y[prev good before src])) (fm.c:130-132,141): src = n when n is good
-        float2 ys = ybuf[o], st = old_state;  // old_state is already conj(previous block's last good sample)
-        bool have = true, cj = false;
-        if (g && gp) {
-          if (o > 0) {
-            st = ybuf[o - 1];
-            cj = true;
-          }
+    if (all_good) {
+      // Uniform fast path (a separate loop on purpose: merged with the general one the compiler predicates the
+      // blanking logic and every sample pays for it). audio[n] = arg(y[n] * conj(y[n-1])) (fm.c:130-132).
+      {
+        const float a0 = fm_arg(ybuf[t], t ? make_float2(ybuf[t - 1].x, -ybuf[t - 1].y) : old_state);
+        aud[t] = a0;
+        fsum = a0;
+        if (t) {
+          pos = a0;
+          neg = a0;
         } else {
-          const int src = g ? o : prev_good(sh.good, o);
-          have = src >= 0;  // no good sample yet in this block: repeat the carried audio value
-          if (have) {
-            ys = ybuf[src];
-            const int pg = prev_good(sh.good, src);
-            if (pg >= 0) {
-              st = ybuf[pg];
-              cj = true;
-            }
-          }
+          sh.scal[0] = a0;
         }
-        if (cj) st.y = -st.y;
-        const float audio = have ? fm_arg(ys, st) : old_last;
+      }
+#pragma unroll 2
+      for (int o = t + 128; o < olen; o += FFT2048_THREADS) {
+        const float2 yp = ybuf[o - 1];
+        const float audio = fm_arg(ybuf[o], make_float2(yp.x, -yp.y));
         aud[o] = audio;
         fsum += audio;
-        if (g && o > 0) {
-          pos = fmaxf(pos, audio);
-          neg = fminf(neg, audio);
+        pos = fmaxf(pos, audio);
+        neg = fminf(neg, audio);
+      }
+      if (t == ((olen - 1) & 127)) sh.scal[1] = aud[olen - 1];  // this thread wrote it
+    } else {
+      const int lane = t & 31;
+#pragma unroll 1
+      for (int i = 0; i < 8; i++) {
+        const int o = t + 128 * i;
+        if (o < olen) {
+          const unsigned wbits = sh.good[o >> 5];
+          const bool g = (wbits >> lane) & 1u;
+          const bool gp = lane ? ((wbits >> (lane - 1)) & 1u) : (o ? (sh.good[(o >> 5) - 1] >> 31) : 1u);
+          // audio[n] = arg(y[src] * conj(y[prev good before src])) (fm.c:130-132,141): src = n when n is good
+          float2 ys = ybuf[o], st = old_state;  // old_state is already conj(previous block's last good sample)
+          bool have = true, cj = false;
+          if (g && gp) {
+            if (o > 0) {
+              st = ybuf[o - 1];
+              cj = true;
+            }
+          } else {
+            const int src = g ? o : prev_good(sh.good, o);
+            have = src >= 0;  // no good sample yet in this block: repeat the carried audio value
+            if (have) {
+              ys = ybuf[src];
+              const int pg = prev_good(sh.good, src);
+              if (pg >= 0) {
+                st = ybuf[pg];
+                cj = true;
+              }
+            }
+          }
+          if (cj) st.y = -st.y;
+          const float audio = have ? fm_arg(ys, st) : old_last;
+          aud[o] = audio;
+          fsum += audio;
+          if (g && o > 0) {
+            pos = fmaxf(pos, audio);
+            neg = fminf(neg, audio);
+          }
+          if (o == 0) sh.scal[0] = g ? audio : 0.f;
+          if (o == olen - 1) sh.scal[1] = audio;
         }
-        if (o == 0) sh.scal[0] = g ? audio : 0.f;
-        if (o == olen - 1) sh.scal[1] = audio;
       }
     }
     block_reduce3<1>(fsum, pos, neg, sh.red);
@@ -351,7 +401,8 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
     st.pdeviation = pdeviation;
     st.agc_gain = sh.P[h].fm_gain;
     st.squelch_open = open ? 1 : 0;
-    st.reserved[0] = st.reserved[1] = 0.f;
+    st.reserved[0] = dbg_allgood;  // 1: no sample was blanked in this block, 0: some were, -1: squelch shut
+    st.reserved[1] = 0.f;
     a.status[(long long)b * a.nchan_total + c] = st;
   }
 }
@@ -441,8 +492,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
         float ssq, samp, minsq;
         const int e = sh.ephase[h];
         __syncthreads();  // every thread has read its stage-3 inputs; the buffer can take the output
-        store16(v, sh.buf, jb);
-        kept_stats(sh.buf, first, &ssq, &samp, &minsq);
+        store16_stats(v, sh.buf, first, &ssq, &samp, &minsq);
         fm_discriminate(a, sh, h, c, b, ssq, samp, minsq, phase_from_index(a, e), h ? sh.aux1 : sh.aux0);
         if (t == 0) sh.ephase[h] = phase_advance(e, sh.P[h].phase_step, a.N);
       } else if (job == 2) {
@@ -458,15 +508,13 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
         int16_t* pa = pcm_row + sh.P[0].pcm_off - first;
         int16_t* pb = pcm_row + sh.P[1].pcm_off - first;
         const bool haveB = wk.y >= 0;
-        __syncthreads();
-        store16(v, sh.buf, jb);
-        // each thread converts the samples it stored itself (n = t + 128j): no barrier needed in between
-#pragma unroll 2
-        for (int n = t + 128 * jb; n < NDEC; n += FFT2048_THREADS) {
-          if (n >= first) {
-            const float2 z = sh.buf[n];
-            pa[n] = scaleclip(z.x * gA);  // fm.c:169-170
-            if (haveB) pb[n] = scaleclip(z.y * gB);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          if (j >= jb) {  // warp-uniform; straight from the registers, no shared-memory round trip
+            if ((j > jb) || (t >= rem)) {
+              pa[t + 128 * j] = scaleclip(v[j].x * gA);  // fm.c:169-170
+              if (haveB) pb[t + 128 * j] = scaleclip(v[j].y * gB);
+            }
           }
         }
       }
@@ -488,198 +536,246 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
   }
 }
 
-// ---------------------------------------------------------------- AM (envelope)
+// ---------------------------------------------------------------- AM (envelope) and linear (SSB / CW / IQ / ISB)
+//
+// Both end in a strictly serial per-sample recurrence (hang AGC, and AM's carrier-DC tracker: am.c:60-74,
+// linear.c:269-280) that must keep the reference's operation order. One lane can only retire ~1 sample per 25 cycles, so
+// a CTA carries AGC_G channels: the parallel parts (response multiply, inverse FFT, amplitudes, quantisation) are done
+// channel after channel by all 128 threads, then lane 0 of warp g runs channel g's recurrence — AGC_G serial loops side
+// by side, each in its own warp so their branches never diverge against each other.
 
-__global__ void __launch_bounds__(FFT2048_THREADS, 4) am_kernel(const ChanLaunch a) {
-  __shared__ CtaShared sh;
+// AGC_G channels per CTA (<= 4 = warps per CTA). Few channels: 1 per CTA minimises latency on a mostly idle GPU; many
+// channels: 4 per CTA amortises the serial phases and maximises throughput. The launcher picks.
+
+template <int AGC_G>
+struct AgcShared {
+  float2 buf[NDEC];            // FFT exchange buffer
+  float amp[AGC_G][1024];      // amplitude (AM: envelope s[n])
+  float qg[AGC_G][1024];       // attack value headroom/x[n] precomputed in parallel; overwritten by gain[n]
+  float red[16];
+  float scal[4][4];
+  // dynamic tail: AM: dc[g][1024] floats; linear: kept samples y[g][1024] float2
+};
+
+template <bool LINEAR, int AGC_G>
+__global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3) : 4) agc_kernel(const ChanLaunch a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  AgcShared<AGC_G>& sh = *reinterpret_cast<AgcShared<AGC_G>*>(smraw);
+  float2* ykeep = reinterpret_cast<float2*>(smraw + sizeof(AgcShared<AGC_G>));  // [AGC_G][1024], LINEAR only
+  float* dcv = reinterpret_cast<float*>(smraw + sizeof(AgcShared<AGC_G>));      // [AGC_G][1024], AM only
   const int t = threadIdx.x;
-  const int c = a.work[blockIdx.x].x;
-  const ChanParams P = a.params[c];
-  ChanState S = a.state[c];
+  const int warp = t >> 5;
   const int olen = a.olen;
   const int first = NDEC - olen;
-  const float2* ybuf = sh.buf + first;  // kept samples y[0..olen)
-  int eph = phase_index0(P.bin, a.start0, a.N);
-  float2 v[16];
-#pragma unroll 1
-  for (int b = 0; b < a.nblocks; b++) {
-    float ssq, samp;
-    stage_filtered<false>(a.spec + (long long)b * a.spec_stride, a.N, (int)P.bin, a.resp + (long long)c * NDEC, sh.buf);
-    __syncthreads();
-    load16(v, sh.buf);
-    fft2048<+1>(v, sh.buf, a.tw2048);
-    __syncthreads();
-    store16(v, sh.buf, first >> 7);
-    // envelope detection ignores the block's LO phase; only the captured filter output carries it
-    float minsq;
-    kept_stats(sh.buf, first, &ssq, &samp, &minsq);
-    __syncthreads();
-    if (a.filt_dbg)
-      dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen, phase_from_index(a, eph));
-    eph = phase_advance(eph, P.phase_step, a.N);
-    for (int o = t; o < olen; o += FFT2048_THREADS) {
-      const float2 y = ybuf[o];
-      sh.aux0[o] = sqrtf(y.x * y.x + y.y * y.y);  // am.c:56-58
-    }
-    float d0 = 0.f, d1 = 0.f;
-    block_reduce3<0>(ssq, d0, d1, sh.red);  // includes the barrier publishing aux0
-    const float signal = ssq;
-    if (t == 0) {
-      // strictly serial recurrences: carrier-DC tracker and hang AGC (am.c:60-74); one lane, original operation order
-      float gain = S.agc_gain, dc = S.am_dc;
-      int hang = S.hang;
-      const float headroom = P.headroom, rf = P.recovery_factor;
-      const int hangmax = P.hangmax;
-      for (int n = 0; n < olen; n++) {
-        const float s = sh.aux0[n];
-        dc += 0.0001f * (s - dc);
-        if (isnan(gain)) {
-          gain = headroom / dc;
-        } else if (gain * dc > headroom) {
-          gain = headroom / dc;
-          hang = hangmax;
-        } else if (hang != 0) {
-          hang--;
-        } else {
-          gain *= rf;
-        }
-        sh.aux1[n] = (s - dc) * gain;
-      }
-      sh.scal[0] = gain;
-      sh.scal[1] = dc;
-      sh.scal[2] = __int_as_float(hang);
-    }
-    __syncthreads();
-    S.agc_gain = sh.scal[0];
-    S.am_dc = sh.scal[1];
-    S.hang = __float_as_int(sh.scal[2]);
-    int16_t* pcm_row = a.pcm + (long long)b * a.pcm_stride + P.pcm_off;
-    for (int o = t; o < olen; o += FFT2048_THREADS) pcm_row[o] = scaleclip(sh.aux1[o]);
-    if (t == 0) {
-      ChanStatus st;
-      st.bb_power = signal / (2 * olen);  // am.c:78 (noise term is identically 0 there)
-      st.snr = NAN;
-      st.foffset = 0.f;
-      st.pdeviation = 0.f;
-      st.agc_gain = S.agc_gain;
-      st.squelch_open = 1;
-      st.reserved[0] = S.am_dc;
-      st.reserved[1] = 0.f;
-      a.status[(long long)b * a.nchan_total + c] = st;
-    }
-    __syncthreads();
+  const int jb = first >> 7, rem = first & 127;
+  int chan[AGC_G];
+#pragma unroll
+  for (int g = 0; g < AGC_G; g++) {
+    const int w = blockIdx.x * AGC_G + g;
+    chan[g] = w < a.nwork ? a.work[w].x : -1;
   }
-  if (t == 0) a.state[c] = S;
-}
-
-// ---------------------------------------------------------------- linear (SSB / CW / IQ / ISB), no PLL
-
-__global__ void __launch_bounds__(FFT2048_THREADS, 4) linear_kernel(const ChanLaunch a) {
-  __shared__ CtaShared sh;
-  const int t = threadIdx.x;
-  const int c = a.work[blockIdx.x].x;
-  const ChanParams P = a.params[c];
-  ChanState S = a.state[c];
-  const int olen = a.olen;
-  const int first = NDEC - olen;
-  const float2* ybuf = sh.buf + first;  // kept samples y[0..olen)
-  int eph = phase_index0(P.bin, a.start0, a.N);
+  // the warp that owns channel g keeps its parameters, state and LO phase index in registers
+  const int myc = warp < AGC_G ? chan[warp < AGC_G ? warp : 0] : -1;
+  ChanParams P;
+  ChanState S;
+  int eph = 0;
+  if (myc >= 0) {
+    P = a.params[myc];
+    S = a.state[myc];
+    eph = phase_index0(P.bin, a.start0, a.N);
+  }
   float2 v[16];
 #pragma unroll 1
   for (int b = 0; b < a.nblocks; b++) {
-    float ssq, samp;
-    if (P.flags & CH_ISB)
-      stage_filtered<true>(a.spec + (long long)b * a.spec_stride, a.N, (int)P.bin, a.resp + (long long)c * NDEC, sh.buf);
-    else
-      stage_filtered<false>(a.spec + (long long)b * a.spec_stride, a.N, (int)P.bin, a.resp + (long long)c * NDEC, sh.buf);
-    __syncthreads();
-    load16(v, sh.buf);
-    fft2048<+1>(v, sh.buf, a.tw2048);
-    __syncthreads();
-    store16(v, sh.buf, first >> 7);
-    float minsq;
-    kept_stats(sh.buf, first, &ssq, &samp, &minsq);
-    const float2 ph = phase_from_index(a, eph);  // applied with the AGC gain below: z = (y * ph) * gain
-    eph = phase_advance(eph, P.phase_step, a.N);
-    __syncthreads();
-    if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen, ph);
-    float sig = 0.f, noi = 0.f, d2 = 0.f;
-    for (int o = t; o < olen; o += FFT2048_THREADS) {
-      const float2 y = ybuf[o];
-      const float rp = y.x * y.x, ip = y.y * y.y;  // linear.c:256-259
-      sig += rp;
-      noi += ip;
-      sh.aux0[o] = sqrtf(rp + ip);
+    const float2* X = a.spec + (long long)b * a.spec_stride;
+    // ---- parallel part, one channel at a time ----
+#pragma unroll 1
+    for (int g = 0; g < AGC_G; g++) {
+      const int c = chan[g];
+      if (c < 0) continue;
+      const int bin = (int)a.params[c].bin;
+      const bool isb = LINEAR && (a.params[c].flags & CH_ISB);
+      if (isb)
+        stage_filtered<true>(X, a.N, bin, a.resp + (long long)c * NDEC, sh.buf);
+      else
+        stage_filtered<false>(X, a.N, bin, a.resp + (long long)c * NDEC, sh.buf);
+      __syncthreads();
+      load16(v, sh.buf);
+      fft2048<+1>(v, sh.buf, a.tw2048);
+      // amplitudes (am.c:56-58, linear.c:256-261) and block power straight from the registers
+      float sig = 0.f, noi = 0.f, dummy = 0.f;
+      float* ampg = sh.amp[g] - first + t;
+      float2* yk = ykeep + g * 1024 - first + t;
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        if (j >= jb) {  // warp-uniform
+          if ((j > jb) || (t >= rem)) {
+            const float rp = v[j].x * v[j].x, ip = v[j].y * v[j].y;
+            sig += rp;
+            noi += ip;
+            ampg[128 * j] = sqrtf(rp + ip);
+            if (LINEAR) yk[128 * j] = v[j];
+          }
+        }
+      }
+      if (a.filt_dbg) {
+        __syncthreads();
+        store16(v, sh.buf, jb);
+        __syncthreads();
+        const int e0 = phase_index0(a.params[c].bin, a.start0, a.N);
+        int e = e0;
+        for (int i = 0; i < b; i++) e = phase_advance(e, a.params[c].phase_step, a.N);
+        dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, sh.buf + first, olen,
+                           phase_from_index(a, e));
+      }
+      block_reduce3<0>(sig, noi, dummy, sh.red);  // also orders the exchange buffer for the next channel
+      if (t == 0) {
+        sh.scal[g][0] = sig;
+        sh.scal[g][1] = noi;
+      }
     }
-    block_reduce3<0>(sig, noi, d2, sh.red);
-    const float signal = sig, noise = noi;
-    if (t == 0) {
-      // hang AGC (linear.c:269-280): serial, one lane, original operation order
+    __syncthreads();
+    // ---- serial part, split so that only true dependences stay on the critical path ----
+    // (1) AM: the carrier-DC tracker is its own recurrence, independent of the gain (am.c:60): one lane per channel,
+    //     an FADD+FFMA chain. (2) The attack value headroom/x[n] (x = dc for AM, amplitude for linear) does not depend on
+    //     the AGC state, so all threads compute those IEEE divisions in parallel. (3) The gain/hang recurrence itself
+    //     (am.c:62-73, linear.c:269-279) is then compare + select per sample, same operands and order as the reference.
+    if (!LINEAR) {
+      if ((t & 31) == 0 && myc >= 0) {
+        const float* am = sh.amp[warp];
+        float* dco = dcv + warp * 1024;
+        float dc = S.am_dc;
+        // explicit batches of 8: all loads first, the FADD+FFMA chain, then the stores (the arrays could alias for
+        // the compiler, which otherwise serialises every load behind the previous store)
+        int n = 0;
+        for (; n + 8 <= olen; n += 8) {
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) x[i] = am[n + i];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            dc += 0.0001f * (x[i] - dc);
+            x[i] = dc;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i++) dco[n + i] = x[i];
+        }
+        for (; n < olen; n++) {
+          dc += 0.0001f * (am[n] - dc);
+          dco[n] = dc;
+        }
+        S.am_dc = dc;
+      }
+      __syncthreads();
+    }
+#pragma unroll 1
+    for (int g = 0; g < AGC_G; g++) {
+      if (chan[g] < 0) continue;
+      const float headroom = a.params[chan[g]].headroom;
+      const float* xs = LINEAR ? sh.amp[g] : dcv + g * 1024;
+      for (int o = t; o < olen; o += FFT2048_THREADS) sh.qg[g][o] = headroom / xs[o];
+    }
+    __syncthreads();
+    if ((t & 31) == 0 && myc >= 0) {
+      const float* xs = LINEAR ? sh.amp[warp] : dcv + warp * 1024;
+      float* qg = sh.qg[warp];
       float gain = S.agc_gain;
       int hang = S.hang;
       const float headroom = P.headroom, rf = P.recovery_factor;
       const int hangmax = P.hangmax;
-      for (int n = 0; n < olen; n++) {
-        const float amplitude = sh.aux0[n];
-        if (isnan(gain)) {
-          gain = headroom / amplitude;
-        } else if (amplitude * gain > headroom) {
-          gain = headroom / amplitude;
-          hang = hangmax;
-        } else if (hang != 0) {
-          hang--;
-        } else {
-          gain *= rf;
+      auto agc_step = [&](float x, float q) {
+        const bool startup = isnan(gain);                     // am.c:64 / linear.c:269: gain = headroom/x, hang untouched
+        const bool over = !startup && (x * gain > headroom);  // attack: gain = headroom/x, hang = hangmax
+        const bool hold = !startup && !over && hang != 0;
+        const float grown = gain * rf;
+        gain = (startup || over) ? q : (hold ? gain : grown);
+        hang = over ? hangmax : (hold ? hang - 1 : hang);
+        return gain;
+      };
+      int n = 0;
+      for (; n + 8 <= olen; n += 8) {  // batches of 8: loads, chain, stores (see the DC tracker above)
+        float x[8], q[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          x[i] = xs[n + i];
+          q[i] = qg[n + i];
         }
-        sh.aux1[n] = gain;
+#pragma unroll
+        for (int i = 0; i < 8; i++) q[i] = agc_step(x[i], q[i]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) qg[n + i] = q[i];
       }
-      sh.scal[0] = gain;
-      sh.scal[2] = __int_as_float(hang);
-    }
-    __syncthreads();
-    S.agc_gain = sh.scal[0];
-    S.hang = __float_as_int(sh.scal[2]);
-    int16_t* pcm_row = a.pcm + (long long)b * a.pcm_stride + P.pcm_off;
-    const bool shifted = P.shift_cycles != 0.0;
-    for (int o = t; o < olen; o += FFT2048_THREADS) {
-      const float g = sh.aux1[o];
-      const float2 y = cmul(ybuf[o], ph);
-      float2 z = make_float2(y.x * g, y.y * g);  // linear.c:280
-      if (shifted) {
-        // post-detection shift oscillator (linear.c:283-289, osc.c:39-51): phasor(n) = exp(j*2*pi*f*n), n counted
-        // from the first sample the oscillator was stepped on
-        double ph = S.shift_phase + P.shift_cycles * (double)o;
-        ph -= floor(ph);
-        double sn, cs;
-        sincospi(2.0 * ph, &sn, &cs);
-        z = cmul(z, make_float2((float)cs, (float)sn));
-      }
-      if (P.channels == 1) {
-        pcm_row[o] = scaleclip(z.x);  // linear.c:291-296
-      } else {
-        pcm_row[2 * o] = scaleclip(z.x);  // I left, Q right (linear.c:299)
-        pcm_row[2 * o + 1] = scaleclip(z.y);
-      }
-    }
-    if (shifted) {
-      double ph = S.shift_phase + P.shift_cycles * (double)olen;
-      S.shift_phase = ph - floor(ph);
-    }
-    if (t == 0) {
+      for (; n < olen; n++) qg[n] = agc_step(xs[n], qg[n]);
+      S.agc_gain = gain;
+      S.hang = hang;
       ChanStatus st;
-      st.bb_power = (signal + noise) / (2 * olen);  // linear.c:302
-      st.snr = NAN;                                 // linear.c:309 (no PLL)
+      const float sig = sh.scal[warp][0], noi = sh.scal[warp][1];
+      st.bb_power = (sig + noi) / (2 * olen);  // am.c:78, linear.c:302
+      st.snr = NAN;                            // linear.c:309 (no PLL)
       st.foffset = 0.f;
       st.pdeviation = 0.f;
-      st.agc_gain = S.agc_gain;
+      st.agc_gain = gain;
       st.squelch_open = 1;
-      st.reserved[0] = signal;
-      st.reserved[1] = noise;
-      a.status[(long long)b * a.nchan_total + c] = st;
+      st.reserved[0] = LINEAR ? sig : S.am_dc;
+      st.reserved[1] = LINEAR ? noi : 0.f;
+      a.status[(long long)b * a.nchan_total + myc] = st;
     }
     __syncthreads();
+    // ---- parallel output: gain / shift / quantise (linear.c:280-299, am.c:74, audio.c:22-28) ----
+    // every warp's lane 0 holds its channel's phase index; publish the per-channel scalars the output loop needs
+    if ((t & 31) == 0 && myc >= 0 && LINEAR) {
+      const float2 ph = phase_from_index(a, eph);
+      sh.scal[warp][2] = ph.x;
+      sh.scal[warp][3] = ph.y;
+    }
+    if (LINEAR) __syncthreads();
+#pragma unroll 1
+    for (int g = 0; g < AGC_G; g++) {
+      const int c = chan[g];
+      if (c < 0) continue;
+      int16_t* pcm_row = a.pcm + (long long)b * a.pcm_stride + a.params[c].pcm_off;
+      if (!LINEAR) {
+        const float* dcg = dcv + g * 1024;
+        for (int o = t; o < olen; o += FFT2048_THREADS)
+          pcm_row[o] = scaleclip((sh.amp[g][o] - dcg[o]) * sh.qg[g][o]);  // am.c:74
+      } else {
+        const float2 ph = make_float2(sh.scal[g][2], sh.scal[g][3]);
+        const double shift_cycles = a.params[c].shift_cycles;
+        const bool shifted = shift_cycles != 0.0;
+        const double phase0 = shifted ? a.state[c].shift_phase + shift_cycles * (double)olen * b : 0.0;
+        const int nch = a.params[c].channels;
+        for (int o = t; o < olen; o += FFT2048_THREADS) {
+          const float gn = sh.qg[g][o];
+          const float2 y = cmul(ykeep[g * 1024 + o], ph);  // the block's LO phase rides the gain multiply
+          float2 z = make_float2(y.x * gn, y.y * gn);      // linear.c:280
+          if (shifted) {
+            // post-detection shift oscillator (linear.c:283-289, osc.c:39-51): phasor(n) = exp(j*2*pi*f*n), n counted
+            // from the first sample the oscillator was stepped on
+            double p = phase0 + shift_cycles * (double)o;
+            p -= floor(p);
+            double sn, cs;
+            sincospi(2.0 * p, &sn, &cs);
+            z = cmul(z, make_float2((float)cs, (float)sn));
+          }
+          if (nch == 1) {
+            pcm_row[o] = scaleclip(z.x);  // linear.c:291-296
+          } else {
+            pcm_row[2 * o] = scaleclip(z.x);  // I left, Q right (linear.c:299)
+            pcm_row[2 * o + 1] = scaleclip(z.y);
+          }
+        }
+      }
+    }
+    if (myc >= 0) eph = phase_advance(eph, P.phase_step, a.N);
+    __syncthreads();
   }
-  if (t == 0) a.state[c] = S;
+  if ((t & 31) == 0 && myc >= 0) {
+    if (LINEAR && P.shift_cycles != 0.0) {
+      double ph = S.shift_phase + P.shift_cycles * (double)olen * a.nblocks;
+      S.shift_phase = ph - floor(ph);
+    }
+    a.state[myc] = S;
+  }
 }
 
 // ---------------------------------------------------------------- launchers
@@ -689,22 +785,32 @@ int launch_fm(const ChanLaunch& a, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(fm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(am_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(linear_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   fm_kernel<<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
-int launch_am(const ChanLaunch& a, cudaStream_t st) {
-  if (a.nwork <= 0) return 0;
-  am_kernel<<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
+template <bool LINEAR, int G>
+static int launch_agc_g(const ChanLaunch& a, cudaStream_t st) {
+  const size_t smem = sizeof(AgcShared<G>) + (LINEAR ? sizeof(float2) : sizeof(float)) * G * 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(agc_kernel<LINEAR, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(agc_kernel<LINEAR, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  agc_kernel<LINEAR, G><<<(a.nwork + G - 1) / G, FFT2048_THREADS, smem, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
-int launch_linear(const ChanLaunch& a, cudaStream_t st) {
+template <bool LINEAR>
+static int launch_agc(const ChanLaunch& a, cudaStream_t st) {
   if (a.nwork <= 0) return 0;
-  linear_kernel<<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  // one channel per CTA until the GPU (148 SMs x ~3 CTAs) is full, then pack to amortise the serial phases
+  if (a.nwork >= 148 * 3 * 2) return launch_agc_g<LINEAR, 4>(a, st);
+  if (a.nwork >= 148 * 3) return launch_agc_g<LINEAR, 2>(a, st);
+  return launch_agc_g<LINEAR, 1>(a, st);
 }
+int launch_am(const ChanLaunch& a, cudaStream_t st) { return launch_agc<false>(a, st); }
+int launch_linear(const ChanLaunch& a, cudaStream_t st) { return launch_agc<true>(a, st); }
 
 }  // namespace k9

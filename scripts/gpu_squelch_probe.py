@@ -18,3 +18,20 @@ for k in range(0, 512, 37):
     y = c.filter_output(k, 4)[2]; a = np.abs(y); bad += int((a*a < 0.3025*a.mean()**2).any())
 print("channels with any blanked sample (of 14 probed):", bad)
 print("pcm rms", pcm.astype(float).std())
+plan = bench.make_plan("cfg5", None)
+iq = bench.make_input(plan, 4)
+c = ch.Channelizer(plan.samprate, plan.L, plan.M, plan.D, max_blocks=4)
+for s in plan.channels: c.add_channel(s.mode, s.bin, low=s.low, high=s.high)
+c.commit()
+for it in range(3):
+    pcm, st = c.process(iq)
+    r = st["reserved"][:, :, 0]
+    print("iter", it, "squelch open", st["squelch_open"].mean(), "all_good frac per block", (r == 1).mean(axis=1), "snr median", np.median(st["snr"]))
+import ctypes as C
+st_buf = (ch._lib.ChanStatus * (4 * c.nchan))()
+pcm2 = np.empty((4, c.pcm_stride), dtype=np.int16)
+for it in range(3):
+    c.compute_resident(4); c.fetch(4, pcm2.ctypes.data_as(C.c_void_p), C.cast(st_buf, C.c_void_p)); c.sync()
+    st = np.frombuffer(st_buf, dtype=np.dtype(ch._lib.ChanStatus)).reshape(4, c.nchan)
+    r = st["reserved"][:, :, 0]
+    print("resident iter", it, "open", st["squelch_open"].mean(), "all_good per block", (r == 1).mean(axis=1))
