@@ -251,14 +251,79 @@ __device__ __forceinline__ float fm_arg(float2 y, float2 st) {
   return fast_atan2f(im, re);
 }
 
+// Cold path of the discriminator, kept out of line so it does not sit in the hot loop's instruction-cache footprint:
+// some sample of the block is below the blanking threshold (fm.c:121,130,141). Builds the good-sample bitmap (one
+// ballot per 32 samples), then audio[n] = arg(y[src] * conj(y[prev good before src])), src = last good sample <= n.
+__device__ __noinline__ void fm_discriminate_blanked(const float2* __restrict__ ybuf, int olen, float min_ampl,
+                                                     float2 old_state, float old_last, float* __restrict__ aud,
+                                                     unsigned* good, float* scal, float* fsum_out, float* pos_out,
+                                                     float* neg_out) {
+  const int t = threadIdx.x;
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) {
+    const int o = t + 128 * i;
+    bool g = false;
+    if (o < olen) {
+      const float2 y = ybuf[o];
+      g = (y.x * y.x + y.y * y.y) > min_ampl;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, g);
+    if ((t & 31) == 0) good[(t >> 5) + 4 * i] = mask;
+  }
+  __syncthreads();
+  float fsum = 0.f, pos = -INFINITY, neg = INFINITY;
+  const int lane = t & 31;
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) {
+    const int o = t + 128 * i;
+    if (o < olen) {
+      const unsigned wbits = good[o >> 5];
+      const bool g = (wbits >> lane) & 1u;
+      const bool gp = lane ? ((wbits >> (lane - 1)) & 1u) : (o ? (good[(o >> 5) - 1] >> 31) : 1u);
+      float2 ys = ybuf[o], st = old_state;  // old_state is already conj(previous block's last good sample)
+      bool have = true, cj = false;
+      if (g && gp) {
+        if (o > 0) {
+          st = ybuf[o - 1];
+          cj = true;
+        }
+      } else {
+        const int src = g ? o : prev_good(good, o);
+        have = src >= 0;  // no good sample yet in this block: repeat the carried audio value
+        if (have) {
+          ys = ybuf[src];
+          const int pg = prev_good(good, src);
+          if (pg >= 0) {
+            st = ybuf[pg];
+            cj = true;
+          }
+        }
+      }
+      if (cj) st.y = -st.y;
+      const float audio = have ? fm_arg(ys, st) : old_last;
+      aud[o] = audio;
+      fsum += audio;
+      if (g && o > 0) {
+        pos = fmaxf(pos, audio);
+        neg = fminf(neg, audio);
+      }
+      if (o == 0) scal[0] = g ? audio : 0.f;
+      if (o == olen - 1) scal[1] = audio;
+    }
+  }
+  *fsum_out = fsum;
+  *pos_out = pos;
+  *neg_out = neg;
+}
+
 // Squelch + discriminator for one channel-block whose kept samples (without the block's LO phase ph) are in sh.buf
 // (fm.c:86-160). Writes olen audio samples to aud[], updates sh.S[h] and the status row. The discriminator only sees
 // phase differences, so ph enters once: the carried state conj(last good sample) is kept in the true (rotated) domain
 // and moved into / out of this block's unrotated domain with one complex multiply each way.
-__device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& sh, int h, int c, int b, float ssq,
-                                                float samp, float minsq, float2 ph, float* __restrict__ aud) {
+__device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& sh, const int olen, int h, int c, int b,
+                                                float ssq, float samp, float minsq, float2 ph,
+                                                float* __restrict__ aud) {
   const int t = threadIdx.x;
-  const int olen = a.olen;
   const float2* ybuf = sh.buf + (NDEC - olen);  // kept samples y[0..olen)
   block_reduce3<2>(ssq, samp, minsq, sh.red);
   if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen, ph);
@@ -283,21 +348,6 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
     const float old_last = sh.S[h].fm_lastaudio;
     const bool all_good = minsq > min_ampl;  // every sample passes the blanking threshold (the usual case)
     dbg_allgood = all_good ? 1.f : 0.f;
-    if (!all_good) {
-      // good-sample bitmap, one ballot per 32 samples
-#pragma unroll 2
-      for (int i = 0; i < 8; i++) {
-        const int o = t + 128 * i;
-        bool g = false;
-        if (o < olen) {
-          const float2 y = ybuf[o];
-          g = (y.x * y.x + y.y * y.y) > min_ampl;
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, g);
-        if ((t & 31) == 0) sh.good[(t >> 5) + 4 * i] = mask;
-      }
-      __syncthreads();
-    }
     float fsum = 0.f, pos = -INFINITY, neg = INFINITY;
     if (all_good) {
       // Uniform fast path (a separate loop on purpose: merged with the general one the compiler predicates the
@@ -324,46 +374,7 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
       }
       if (t == ((olen - 1) & 127)) sh.scal[1] = aud[olen - 1];  // this thread wrote it
     } else {
-      const int lane = t & 31;
-#pragma unroll 1
-      for (int i = 0; i < 8; i++) {
-        const int o = t + 128 * i;
-        if (o < olen) {
-          const unsigned wbits = sh.good[o >> 5];
-          const bool g = (wbits >> lane) & 1u;
-          const bool gp = lane ? ((wbits >> (lane - 1)) & 1u) : (o ? (sh.good[(o >> 5) - 1] >> 31) : 1u);
-          // audio[n] = arg(y[src] * conj(y[prev good before src])) (fm.c:130-132,141): src = n when n is good
-          float2 ys = ybuf[o], st = old_state;  // old_state is already conj(previous block's last good sample)
-          bool have = true, cj = false;
-          if (g && gp) {
-            if (o > 0) {
-              st = ybuf[o - 1];
-              cj = true;
-            }
-          } else {
-            const int src = g ? o : prev_good(sh.good, o);
-            have = src >= 0;  // no good sample yet in this block: repeat the carried audio value
-            if (have) {
-              ys = ybuf[src];
-              const int pg = prev_good(sh.good, src);
-              if (pg >= 0) {
-                st = ybuf[pg];
-                cj = true;
-              }
-            }
-          }
-          if (cj) st.y = -st.y;
-          const float audio = have ? fm_arg(ys, st) : old_last;
-          aud[o] = audio;
-          fsum += audio;
-          if (g && o > 0) {
-            pos = fmaxf(pos, audio);
-            neg = fminf(neg, audio);
-          }
-          if (o == 0) sh.scal[0] = g ? audio : 0.f;
-          if (o == olen - 1) sh.scal[1] = audio;
-        }
-      }
+      fm_discriminate_blanked(ybuf, olen, min_ampl, old_state, old_last, aud, sh.good, sh.scal, &fsum, &pos, &neg);
     }
     block_reduce3<1>(fsum, pos, neg, sh.red);
     const float init = sh.scal[0];
@@ -407,6 +418,19 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& 
   }
 }
 
+// FLAT mode: the raw discriminator output goes out unfiltered and unscaled (fm.c:55,164-172). Cold, out of line.
+__device__ __noinline__ void fm_flat_output(const float* audA, const float* audB, int16_t* pa, int16_t* pb, int olen) {
+  __syncthreads();
+#pragma unroll 1
+  for (int o = threadIdx.x; o < olen; o += FFT2048_THREADS) {
+    pa[o] = scaleclip(audA[o]);
+    if (pb) pb[o] = scaleclip(audB[o]);
+  }
+}
+
+// OLEN_T: output samples per block known at compile time (960 = the reference geometry at every input rate, SURVEY
+// Appendix B) so the kept-row tests fold away; 0 = take it from the launch arguments.
+template <int OLEN_T>
 __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(const ChanLaunch a) {
   __shared__ CtaShared sh;
   const int t = threadIdx.x;
@@ -420,7 +444,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
     }
   }
   __syncthreads();
-  const int olen = a.olen;
+  const int olen = OLEN_T ? OLEN_T : a.olen;
   const int first = NDEC - olen;
   const int jb = first >> 7, rem = first & 127;
   const bool filtered = sh.P[0].audio_slot >= 0;
@@ -493,7 +517,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
         const int e = sh.ephase[h];
         __syncthreads();  // every thread has read its stage-3 inputs; the buffer can take the output
         store16_stats(v, sh.buf, first, &ssq, &samp, &minsq);
-        fm_discriminate(a, sh, h, c, b, ssq, samp, minsq, phase_from_index(a, e), h ? sh.aux1 : sh.aux0);
+        fm_discriminate(a, sh, olen, h, c, b, ssq, samp, minsq, phase_from_index(a, e), h ? sh.aux1 : sh.aux0);
         if (t == 0) sh.ephase[h] = phase_advance(e, sh.P[h].phase_step, a.N);
       } else if (job == 2) {
         const float2* R = a.audio_resp + (long long)sh.P[0].audio_slot * NDEC + t;
@@ -519,15 +543,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
         }
       }
     }
-    if (!filtered) {
-      // FLAT: raw discriminator output goes out unfiltered and unscaled (fm.c:55,164-172)
-      __syncthreads();
-#pragma unroll 1
-      for (int o = t; o < olen; o += FFT2048_THREADS) {
-        pcm_row[sh.P[0].pcm_off + o] = scaleclip(sh.aux0[o]);
-        if (wk.y >= 0) pcm_row[sh.P[1].pcm_off + o] = scaleclip(sh.aux1[o]);
-      }
-    }
+    if (!filtered) fm_flat_output(sh.aux0, sh.aux1, pcm_row + sh.P[0].pcm_off, wk.y >= 0 ? pcm_row + sh.P[1].pcm_off : nullptr, olen);
     __syncthreads();
   }
   if (t < 2) {
@@ -557,7 +573,7 @@ struct AgcShared {
   // dynamic tail: AM: dc[g][1024] floats; linear: kept samples y[g][1024] float2
 };
 
-template <bool LINEAR, int AGC_G>
+template <bool LINEAR, int AGC_G, int OLEN_T>
 __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3) : 4) agc_kernel(const ChanLaunch a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   AgcShared<AGC_G>& sh = *reinterpret_cast<AgcShared<AGC_G>*>(smraw);
@@ -565,7 +581,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
   float* dcv = reinterpret_cast<float*>(smraw + sizeof(AgcShared<AGC_G>));      // [AGC_G][1024], AM only
   const int t = threadIdx.x;
   const int warp = t >> 5;
-  const int olen = a.olen;
+  const int olen = OLEN_T ? OLEN_T : a.olen;
   const int first = NDEC - olen;
   const int jb = first >> 7, rem = first & 127;
   int chan[AGC_G];
@@ -604,8 +620,9 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
       fft2048<+1>(v, sh.buf, a.tw2048);
       // amplitudes (am.c:56-58, linear.c:256-261) and block power straight from the registers
       float sig = 0.f, noi = 0.f, dummy = 0.f;
-      float* ampg = sh.amp[g] - first + t;
-      float2* yk = ykeep + g * 1024 - first + t;
+      float* ampg = sh.amp[g];
+      float2* yk = ykeep + g * 1024;
+      const int ko = t - first;  // kept-sample index of row j is ko + 128 j
 #pragma unroll
       for (int j = 0; j < 16; j++) {
         if (j >= jb) {  // warp-uniform
@@ -613,8 +630,8 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
             const float rp = v[j].x * v[j].x, ip = v[j].y * v[j].y;
             sig += rp;
             noi += ip;
-            ampg[128 * j] = sqrtf(rp + ip);
-            if (LINEAR) yk[128 * j] = v[j];
+            ampg[ko + 128 * j] = sqrtf(rp + ip);
+            if (LINEAR) yk[ko + 128 * j] = v[j];
           }
         }
       }
@@ -784,10 +801,14 @@ int launch_fm(const ChanLaunch& a, cudaStream_t st) {
   if (a.nwork <= 0) return 0;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(fm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fm_kernel<960>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fm_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  fm_kernel<<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
+  if (a.olen == 960)
+    fm_kernel<960><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
+  else
+    fm_kernel<0><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 template <bool LINEAR, int G>
@@ -795,11 +816,16 @@ static int launch_agc_g(const ChanLaunch& a, cudaStream_t st) {
   const size_t smem = sizeof(AgcShared<G>) + (LINEAR ? sizeof(float2) : sizeof(float)) * G * 1024;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(agc_kernel<LINEAR, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(agc_kernel<LINEAR, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(agc_kernel<LINEAR, G, 960>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(agc_kernel<LINEAR, G, 960>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(agc_kernel<LINEAR, G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(agc_kernel<LINEAR, G, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  agc_kernel<LINEAR, G><<<(a.nwork + G - 1) / G, FFT2048_THREADS, smem, st>>>(a);
+  if (a.olen == 960)
+    agc_kernel<LINEAR, G, 960><<<(a.nwork + G - 1) / G, FFT2048_THREADS, smem, st>>>(a);
+  else
+    agc_kernel<LINEAR, G, 0><<<(a.nwork + G - 1) / G, FFT2048_THREADS, smem, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 template <bool LINEAR>
