@@ -268,7 +268,9 @@ def run_ours(args, plan):
         i = e2e_count[0]
         e2e_count[0] += 1
         if not multi or rank == 0 or args.mgpu == "allgather":
-            c.push(in_ptr, B)
+            if i == 0:
+                c.push(in_ptr, B)      # prime: batch 0
+            c.push(in_ptr, B)          # batch i+1 goes up while batch i is computed (the ring holds two batches)
         if not multi:
             c.compute(B)
         else:

@@ -500,7 +500,10 @@ int ka9q_stream_push(ka9q_stream* s, const void* iq, int nblocks) {
   // the region about to be overwritten was last read by the compute issued two calls ago
   K9_CHECK(s->pushed + n - s->block0 * (long long)s->cfg.L <= 2LL * s->cfg.max_blocks * s->cfg.L,
            "push would overwrite samples that have not been computed yet");
-  K9_CUDA(cudaStreamWaitEvent(s->s_in, s->e_comp_done[s->comp_parity ^ 1], 0));
+  // The ring holds two batches: this push overwrites the batch before the one most recently handed to compute, so it
+  // must wait for the latest ISSUED compute's predecessor at least; waiting for the latest issued compute itself is
+  // correct for every call order (push k+1 issued before compute k then overlaps compute k).
+  K9_CUDA(cudaStreamWaitEvent(s->s_in, s->e_comp_done[s->comp_parity], 0));
   long long pos = (s->pushed + (s->cfg.M - 1)) % s->ring_cap;
   long long done = 0;
   while (done < n) {
