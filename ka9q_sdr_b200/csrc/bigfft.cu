@@ -135,6 +135,184 @@ __global__ void __launch_bounds__(T*(R1 > R2 ? R1 : R2)) fft_pass_kernel(const P
   }
 }
 
+// ---------------- persistent variant with asynchronous staging (large forward transforms) ----------------
+//
+// Same pass, but the CTAs are persistent and the global->shared copies of tile i+1 are issued with cp.async (LDGSTS) while
+// tile i is transformed, into a per-thread staging area (each thread later reads back exactly the slots it copied, so the
+// staging needs no barrier). ncu on the synchronous kernel showed 7-15 warps per issue slot parked on long_scoreboard and
+// ~1.8 TB/s; this keeps loads in flight during the butterflies without spending registers on them.
+__device__ __forceinline__ void cp_async_bytes(void* smem_dst, const void* gsrc, int bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (bytes == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <int R1, int R2, int T, bool QFAST>
+__global__ void __launch_bounds__(T*(R1 > R2 ? R1 : R2)) fft_pass_async_kernel(const PassArgs a) {
+  constexpr int SIGN = -1;
+  constexpr int R = R1 * R2;
+  constexpr int S = R + 1;     // padded column stride of the exchange buffer (float2 units)
+  constexpr int NA = T * R2;   // threads active in sub-pass A
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float2* sm = reinterpret_cast<float2*>(smraw);                                       // exchange buffer [T*S]
+  unsigned long long* stage = reinterpret_cast<unsigned long long*>(sm + T * S + 1);  // [2][R1][NA] 8-byte slots
+  const int tid = threadIdx.x;
+  const int batch = blockIdx.y;
+  const int s = a.N / a.n_cur;
+  const int ntiles = (a.ncols + T - 1) / T;
+  const bool actA = tid < NA;
+  const int colA = tid % T;
+  const int pA = tid / T;
+  const bool is_c32 = (a.in_mode == IN_C32) || (a.in_mode == IN_RING_C32);
+  const int esz = is_c32 ? 8 : 4;  // IN_RING_S16: short2; IN_RING_R32: float
+  const long long rbase = (a.in_mode == IN_C32) ? 0 : ring_base(a, batch);
+  const char* gbase = reinterpret_cast<const char*>(a.in) +
+                      (a.in_mode == IN_C32 ? (long long)batch * a.in_batch_stride * 8 : 0);
+
+  auto issue = [&](int tile, int buf) {
+    const int c = tile * T + colA;
+    if (actA && c < a.ncols) {
+#pragma unroll
+      for (int r = 0; r < R1; r++) {
+        const int idx = c + a.ncols * (pA + R2 * r);
+        const long long pos = (a.in_mode == IN_C32) ? idx : ring_pos(a, rbase, idx);
+        cp_async_bytes(&stage[(buf * R1 + r) * NA + tid], gbase + pos * esz, esz);
+      }
+    }
+    cp_async_commit();
+  };
+
+  int tile = blockIdx.x;
+  int buf = 0;
+  if (tile < ntiles) issue(tile, 0);
+  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < ntiles)
+      issue(next, buf ^ 1);
+    else
+      cp_async_commit();  // empty group: keeps "all but the newest group" == "this tile" for wait_group<1>
+    cp_async_wait<1>();
+    const int col0 = tile * T;
+    // ---- sub-pass A ----
+    float esum = 0.f;
+    if (actA) {
+      const int c = col0 + colA;
+      if (c < a.ncols) {
+        float2 v[R1];
+#pragma unroll
+        for (int r = 0; r < R1; r++) {
+          const unsigned long long raw = stage[(buf * R1 + r) * NA + tid];
+          float2 x;
+          if (is_c32) {
+            x = make_float2(__uint_as_float((unsigned)raw), __uint_as_float((unsigned)(raw >> 32)));
+          } else if (a.in_mode == IN_RING_S16) {
+            const short lo = (short)(raw & 0xffffu), hi = (short)((raw >> 16) & 0xffffu);
+            // reference radio.c:113-114,122: (float)int16 * SCALE16, then * gain_factor
+            x = make_float2(((float)lo * a.scale) * a.gain, ((float)hi * a.scale) * a.gain);
+          } else {
+            x = make_float2(__uint_as_float((unsigned)raw), 0.f);
+          }
+          v[r] = x;
+          if (a.energy != nullptr && c + a.ncols * (pA + R2 * r) >= a.stat_from) esum += x.x * x.x + x.y * x.y;
+        }
+        Dft<R1, SIGN>::run(v);
+#pragma unroll
+        for (int j = 0; j < R1; j++) {
+          float2 o = v[j];
+          if (j > 0 && pA > 0) o = cmul(o, __ldg(a.tw_r + pA * j));
+          sm[colA * S + R1 * pA + j] = o;
+        }
+      }
+    }
+    if (a.energy != nullptr) {
+      esum = warp_sum(esum);
+      if ((tid & 31) == 0 && esum != 0.f) atomicAdd(a.energy + batch, esum);
+    }
+    __syncthreads();
+    // ---- sub-pass B ----
+    if (tid < T * R1) {
+      const int col = QFAST ? tid / R1 : tid % T;
+      const int q = QFAST ? tid % R1 : tid / T;
+      const int c = col0 + col;
+      if (c < a.ncols) {
+        float2 w[R2];
+#pragma unroll
+        for (int r = 0; r < R2; r++) w[r] = sm[col * S + q + R1 * r];
+        Dft<R2, SIGN>::run(w);
+        const int qg = c % s;
+        const int pg = c / s;
+        float2* out = a.out + (long long)batch * a.out_batch_stride + qg + (long long)s * ((long long)R * pg);
+        const bool last = (a.n_cur == R);
+#pragma unroll
+        for (int j = 0; j < R2; j++) {
+          const int jt = q + R1 * j;
+          float2 o = w[j];
+          if (!last) {
+            const unsigned e = (unsigned)pg * (unsigned)jt * (unsigned)s;  // < N
+            if (e != 0) o = cmul(o, big_twiddle<SIGN>(a, e));
+          }
+          out[(long long)s * jt] = o;
+        }
+      }
+    }
+    __syncthreads();  // the exchange buffer is reused by the next tile
+  }
+  cp_async_wait<0>();
+}
+
+template <int R1, int R2, int T>
+static cudaError_t launch_async_kind(const PassArgs& a, int batch, bool qfast, cudaStream_t st) {
+  constexpr int R = R1 * R2;
+  constexpr int threads = T * (R1 > R2 ? R1 : R2);
+  const size_t smem = sizeof(float2) * ((size_t)T * (R + 1) + 1) + 8ull * 2 * R1 * T * R2;
+  const int ntiles = (a.ncols + T - 1) / T;
+  static int ctas_per_sm = -1;
+  if (ctas_per_sm < 0) {
+    const char* e = getenv("KA9Q_B200_FFT_CTAS");
+    ctas_per_sm = e ? atoi(e) : 4;
+  }
+  int gx = (148 * ctas_per_sm + batch - 1) / batch;  // persistent CTAs per SM over the whole batch
+  if (gx > ntiles) gx = ntiles;
+  dim3 grid(gx, batch);
+  if (qfast) {
+    cudaFuncSetAttribute(fft_pass_async_kernel<R1, R2, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fft_pass_async_kernel<R1, R2, T, true><<<grid, threads, smem, st>>>(a);
+  } else {
+    cudaFuncSetAttribute(fft_pass_async_kernel<R1, R2, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fft_pass_async_kernel<R1, R2, T, false><<<grid, threads, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+// returns cudaErrorNotSupported when this pass should use the synchronous kernel
+static cudaError_t launch_pass_async(int R1, int R2, const PassArgs& a, int batch, int sign, bool qfast, cudaStream_t st) {
+  if (sign >= 0 || a.in_mode == IN_RING_S8) return cudaErrorNotSupported;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("KA9Q_B200_FFT_ASYNC");
+    enabled = e ? atoi(e) : 1;
+  }
+  if (!enabled) return cudaErrorNotSupported;
+#define K9_ACASE(r1, r2, t)                                                                   \
+  if (R1 == r1 && R2 == r2) {                                                                 \
+    if ((long long)((a.ncols + t - 1) / t) * batch < 148 * 3 * 2) return cudaErrorNotSupported; \
+    return launch_async_kind<r1, r2, t>(a, batch, qfast, st);                                 \
+  }
+  K9_ACASE(8, 16, 16)
+  K9_ACASE(10, 16, 16)
+  K9_ACASE(5, 16, 16)
+  K9_ACASE(8, 8, 32)
+#undef K9_ACASE
+  return cudaErrorNotSupported;
+}
+
 // ---------------- host side ----------------
 
 struct PassKind {
@@ -348,7 +526,9 @@ int bigfft_exec(const BigFftPlan* plan, const BigFftIn& in, float2* out, long lo
     a.tw_lo = plan->tw_lo;
     a.tw_hi = plan->tw_hi;
     a.tw_r = plan->tw_r[p];
-    cudaError_t e = launch_pass(plan->R1[p], plan->R2[p], a, batch, sign, /*qfast=*/(N / n_cur) == 1, stream);
+    cudaError_t e = launch_pass_async(plan->R1[p], plan->R2[p], a, batch, sign, /*qfast=*/(N / n_cur) == 1, stream);
+    if (e == cudaErrorNotSupported)
+      e = launch_pass(plan->R1[p], plan->R2[p], a, batch, sign, /*qfast=*/(N / n_cur) == 1, stream);
     if (e != cudaSuccess) {
       fprintf(stderr, "bigfft: launch failed: %s\n", cudaGetErrorString(e));
       return -4;
