@@ -34,7 +34,7 @@ constexpr int FFT2048_TW_FLOAT2 = 2048 + 256;
 template <int SIGN>
 __device__ __forceinline__ float2 tw_mul(float2 a, float wx, float wy) {
   // a * (wx + i*SIGN'*wy) where the table holds the forward twiddle: conjugate it for the backward transform
-  return SIGN > 0 ? make_float2(a.x * wx + a.y * wy, a.y * wx - a.x * wy) : make_float2(a.x * wx - a.y * wy, a.x * wy + a.y * wx);
+  return cmul_xy(a, wx, SIGN > 0 ? -wy : wy);
 }
 
 template <int SIGN>

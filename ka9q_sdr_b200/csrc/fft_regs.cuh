@@ -70,18 +70,55 @@ __host__ __device__ constexpr double cx_sin2pi(long long num, long long den) {
   }
 }
 
-// ---- complex helpers ----
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// ---- complex helpers on packed fp32x2 (sm_100a FADD2 / FMUL2 / FFMA2) ----
+// A complex float is one 64-bit register pair; Blackwell's packed fp32 instructions add/multiply both halves in one
+// issue slot, and their operand modifiers swap halves, negate one half or broadcast a scalar for free. So a complex
+// add is ONE instruction (not two), a complex multiply TWO (not four), and multiplying by +-i costs nothing. The
+// butterflies are ~half of what these kernels execute and the kernels are issue bound, so this is the single largest
+// instruction-count lever. The pack/unpack moves below are register renaming only (ptxas allocates aligned pairs).
+typedef unsigned long long k9_u64;
+__device__ __forceinline__ k9_u64 pk2(float x, float y) {
+  k9_u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
 }
-__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
-  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+__device__ __forceinline__ float2 upk2(k9_u64 v) {
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(v));
+  return d;
 }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  k9_u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+  return upk2(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  k9_u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+  return upk2(r);
+}
+// a * s + b with a real scalar s
+__device__ __forceinline__ float2 cfma_s(float2 a, float s, float2 b) {
+  k9_u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(s, s)), "l"(pk2(b.x, b.y)));
+  return upk2(r);
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s) {
+  k9_u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(s, s)));
+  return upk2(r);
+}
+// a * (bx + i*by): (a.x bx - a.y by, a.y bx + a.x by) = a*bx + (-a.y, a.x)*by
+__device__ __forceinline__ float2 cmul_xy(float2 a, float bx, float by) {
+  k9_u64 t, r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pk2(a.x, a.y)), "l"(pk2(bx, bx)));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(-a.y, a.x)), "l"(pk2(by, by)), "l"(t));
+  return upk2(r);
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return cmul_xy(a, b.x, b.y); }
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return cmul_xy(a, b.x, -b.y); }  // a * conj(b)
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
-__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
-// multiply by exp(SIGN*i*pi/2) = SIGN*i
+// multiply by exp(SIGN*i*pi/2) = SIGN*i (folds into the consumer's operand modifiers)
 template <int SIGN>
 __device__ __forceinline__ float2 mul_i(float2 a) {
   return SIGN > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
@@ -101,7 +138,7 @@ __device__ __forceinline__ float2 mul_tw(float2 a) {
   } else {
     constexpr float c = (float)cx_cos2pi(k, N);
     constexpr float s = (float)(SIGN * cx_sin2pi(k, N));
-    return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+    return cmul_xy(a, c, s);
   }
 }
 
@@ -116,10 +153,9 @@ __device__ __forceinline__ void dft2(float2& a, float2& b) {
 template <int SIGN>
 __device__ __forceinline__ void dft3(float2& a, float2& b, float2& c) {
   constexpr float s60 = (float)(0.86602540378443864676);
-  float2 t1 = cadd(b, c);
-  float2 t2 = make_float2(a.x - 0.5f * t1.x, a.y - 0.5f * t1.y);
-  float2 d = csub(b, c);
-  float2 t3 = mul_i<SIGN>(make_float2(s60 * d.x, s60 * d.y));
+  const float2 t1 = cadd(b, c);
+  const float2 t2 = cfma_s(t1, -0.5f, a);
+  const float2 t3 = mul_i<SIGN>(cscale(csub(b, c), s60));
   a = cadd(a, t1);
   b = cadd(t2, t3);
   c = csub(t2, t3);
@@ -127,8 +163,8 @@ __device__ __forceinline__ void dft3(float2& a, float2& b, float2& c) {
 
 template <int SIGN>
 __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
-  float2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d);
-  float2 jbmd = mul_i<SIGN>(csub(b, d));
+  const float2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d);
+  const float2 jbmd = mul_i<SIGN>(csub(b, d));
   a = cadd(apc, bpd);
   b = cadd(amc, jbmd);
   c = csub(apc, bpd);
@@ -141,13 +177,13 @@ __device__ __forceinline__ void dft5(float2& v0, float2& v1, float2& v2, float2&
   constexpr float c2 = (float)-0.80901699437494742410;  // cos(4pi/5)
   constexpr float s1 = (float)0.95105651629515357212;   // sin(2pi/5)
   constexpr float s2 = (float)0.58778525229247312917;   // sin(4pi/5)
-  float2 a14 = cadd(v1, v4), s14 = csub(v1, v4);
-  float2 a23 = cadd(v2, v3), s23 = csub(v2, v3);
-  float2 r1 = make_float2(v0.x + c1 * a14.x + c2 * a23.x, v0.y + c1 * a14.y + c2 * a23.y);
-  float2 r2 = make_float2(v0.x + c2 * a14.x + c1 * a23.x, v0.y + c2 * a14.y + c1 * a23.y);
-  float2 i1 = mul_i<SIGN>(make_float2(s1 * s14.x + s2 * s23.x, s1 * s14.y + s2 * s23.y));
-  float2 i2 = mul_i<SIGN>(make_float2(s2 * s14.x - s1 * s23.x, s2 * s14.y - s1 * s23.y));
-  v0 = make_float2(v0.x + a14.x + a23.x, v0.y + a14.y + a23.y);
+  const float2 a14 = cadd(v1, v4), s14 = csub(v1, v4);
+  const float2 a23 = cadd(v2, v3), s23 = csub(v2, v3);
+  const float2 r1 = cfma_s(a23, c2, cfma_s(a14, c1, v0));
+  const float2 r2 = cfma_s(a23, c1, cfma_s(a14, c2, v0));
+  const float2 i1 = mul_i<SIGN>(cfma_s(s23, s2, cscale(s14, s1)));
+  const float2 i2 = mul_i<SIGN>(cfma_s(s23, -s1, cscale(s14, s2)));
+  v0 = cadd(v0, cadd(a14, a23));
   v1 = cadd(r1, i1);
   v4 = csub(r1, i1);
   v2 = cadd(r2, i2);
