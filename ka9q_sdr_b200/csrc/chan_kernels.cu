@@ -127,6 +127,37 @@ __device__ __forceinline__ void load16(float2 (&v)[16], const float2* __restrict
 #pragma unroll
     for (int r = 0; r < 8; r++) v[8 * e + r] = bp[128 * e + 256 * r];
 }
+// Filtered spectrum window straight into the transform's input registers (no shared-memory staging): row j = e + 2r of
+// thread t is bin p = t + 128j, v[8e + r] = H[p] * X[(bin + s(p)) mod N], s(p) = p for p <= N_dec/2, else p - N_dec
+// (filter.c:206-227). Consecutive lanes read consecutive bins, so both streams are coalesced.
+__device__ __forceinline__ void load_filtered16(float2 (&v)[16], const float2* __restrict__ X, int N, int bin,
+                                                const float2* __restrict__ H) {
+  const int t = threadIdx.x;
+  int i0 = bin + t;  // rows 0..7: positive frequencies
+  if (i0 < 0) i0 += N;
+  if (i0 >= N) i0 -= N;
+  int i1 = bin + t - 1024;  // rows 8..15: negative frequencies
+  if (i1 < 0) i1 += N;
+  if (i1 >= N) i1 -= N;
+#pragma unroll
+  for (int e = 0; e < 2; e++)
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int j = e + 2 * r;
+      int i = (j < 8 ? i0 : i1) + 128 * (j & 7);
+      if (i >= N) i -= N;
+      if (j == 8 && t == 0) {  // the Nyquist bin belongs to the positive side (filter.c:206: p <= N_dec/2)
+        i = bin + 1024;
+        if (i >= N) i -= N;
+      }
+      v[8 * e + r] = __ldg(X + i);
+    }
+  const float2* Hp = H + t;
+#pragma unroll
+  for (int e = 0; e < 2; e++)
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[8 * e + r] = cmul(__ldg(Hp + 128 * (e + 2 * r)), v[8 * e + r]);
+}
 // transform output -> buffer in natural order: buf[t + 128j] = v[j], only the rows that hold kept samples (j >= jb)
 __device__ __forceinline__ void store16(const float2 (&v)[16], float2* __restrict__ buf, int jb) {
   float2* bp = buf + threadIdx.x;
@@ -468,48 +499,34 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
           for (int o = t; o < olen; o += FFT2048_THREADS) sh.aux1[o] = 0.f;
           continue;
         }
-        stage_filtered<false>(X, a.N, (int)sh.P[h].bin, a.resp + (long long)c * NDEC, sh.buf);
+        load_filtered16(v, X, a.N, (int)sh.P[h].bin, a.resp + (long long)c * NDEC);
       } else if (job == 2) {
         if (!filtered) break;
         // REAL overlap-save input of the post-detection filter, L=olen, M=NDEC-olen+1 (fm.c:39-43): two real channels
         // ride one complex transform, z = audA + j audB (the filter's impulse response is real). History lives in a
         // 2048-sample ring per channel; this block's new samples are appended to it here.
         const int ringbase = (int)(((m + 1) * (long long)olen) & (NDEC - 1));
-        // history rows (p < first): all ring loads in flight first (v[] is dead here, registers are free)
-        {
-          float ha[9], hb[9];
+        // Straight into the transform's input registers: row j = e + 2r of thread t is sample p = t + 128j; history
+        // rows (p < first) come from the ring, the rest are this block's new samples, appended to the ring here.
+        // conj on the way in: forward transform via the backward code.
 #pragma unroll
-          for (int k = 0; k < 9; k++) {
-            const int p = t + 128 * k;
+        for (int e = 0; e < 2; e++)
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const int p = t + 128 * (e + 2 * r);
             const int ri = (ringbase + p) & (NDEC - 1);
-            const bool use = p < first;
-            ha[k] = use ? hist[0][ri] : 0.f;
-            hb[k] = (use && hist[1]) ? hist[1][ri] : 0.f;
+            float za, zb;
+            if (p < first) {
+              za = hist[0][ri];
+              zb = hist[1] ? hist[1][ri] : 0.f;
+            } else {
+              za = sh.aux0[p - first];
+              zb = sh.aux1[p - first];
+              hist[0][ri] = za;
+              if (hist[1]) hist[1][ri] = zb;
+            }
+            v[8 * e + r] = make_float2(za, -zb);
           }
-#pragma unroll
-          for (int k = 0; k < 9; k++) {
-            const int p = t + 128 * k;
-            if (p < first) sh.buf[p] = make_float2(ha[k], -hb[k]);  // conj: forward transform via the backward code
-          }
-        }
-#pragma unroll 1
-        for (int p = t + 128 * 9; p < first; p += FFT2048_THREADS) {  // only when olen < 896
-          const int ri = (ringbase + p) & (NDEC - 1);
-          sh.buf[p] = make_float2(hist[0][ri], hist[1] ? -hist[1][ri] : 0.f);
-        }
-        // new samples: append to the ring and stage
-#pragma unroll 2
-        for (int o = t; o < olen; o += FFT2048_THREADS) {
-          const int ri = (ringbase + first + o) & (NDEC - 1);
-          const float za = sh.aux0[o], zb = sh.aux1[o];
-          hist[0][ri] = za;
-          if (hist[1]) hist[1][ri] = zb;
-          sh.buf[first + o] = make_float2(za, -zb);
-        }
-      }
-      if (job < 3) {
-        __syncthreads();
-        load16(v, sh.buf);
       }
       fft2048<+1>(v, sh.buf, a.tw2048);
       if (job < 2) {
