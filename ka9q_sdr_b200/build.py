@@ -18,6 +18,8 @@ CU_SOURCES = ["bigfft.cu", "chan_kernels.cu", "design.cu", "stream.cu", "dropin.
 C_SOURCES = ["osc_host.c"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default", "--threads", "2"]
+# experiment hook: extra -D switches for kernel variants (e.g. KA9Q_B200_NVCC_EXTRA="-DFM_CTAS_PER_SM=6")
+NVCC_FLAGS += os.environ.get("KA9Q_B200_NVCC_EXTRA", "").split()
 
 
 def _stamp(paths):

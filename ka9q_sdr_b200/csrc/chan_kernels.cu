@@ -20,6 +20,33 @@ namespace k9 {
 
 // ---------------------------------------------------------------- common device helpers
 
+#ifndef FM_STREAM_LOADS
+#define FM_STREAM_LOADS 0
+#endif
+#ifndef FM_ALIAS_AUX1
+#define FM_ALIAS_AUX1 1
+#endif
+// read-once streams (the per-channel response and audio history): keep them out of L1 so the spectrum windows that
+// neighbouring channels share and the twiddle / de-emphasis tables stay resident
+__device__ __forceinline__ float ldg_stream(const float* p) {
+#if FM_STREAM_LOADS
+  float r;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");  // written by this CTA: not .nc
+  return r;
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ float2 ldg_stream(const float2* p) {
+#if FM_STREAM_LOADS
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+#else
+  return __ldg(p);
+#endif
+}
+
 struct CtaShared {
   float2 buf[NDEC];   // FFT exchange buffer; afterwards the olen kept samples y[0..olen)
   float aux0[1024];   // FM: audio of channel A / AM,linear: amplitude
@@ -30,6 +57,26 @@ struct CtaShared {
   int ephase[2];      // (k * block_start) mod N per channel of the work item
   ChanParams P[2];
   ChanState S[2];
+};
+
+// FM pairs with the compile-time geometry (olen = 960): channel B's audio is parked in the part of the exchange buffer
+// that is idle between B's discriminator and the audio transform (bins [0, N_dec - olen) hold nothing then), which
+// brings 8 CTAs under the 196 KB carve-out and leaves ~60 KB of L1 for the shared twiddle / de-emphasis tables.
+template <int OLEN_T>
+struct FmShared {
+  float2 buf[NDEC];
+  float aux0[OLEN_T];
+  float red[16];
+  unsigned good[32];
+  float scal[8];
+  int ephase[2];
+  ChanParams P[2];
+  ChanState S[2];
+  __device__ __forceinline__ float* audio_b() { return reinterpret_cast<float*>(buf); }
+};
+template <>
+struct FmShared<0> : CtaShared {
+  __device__ __forceinline__ float* audio_b() { return aux1; }
 };
 
 // three block-wide reductions in one round trip. MODE 0: sum,sum,sum  1: sum,max,min  2: sum,sum,min
@@ -156,7 +203,7 @@ __device__ __forceinline__ void load_filtered16(float2 (&v)[16], const float2* _
 #pragma unroll
   for (int e = 0; e < 2; e++)
 #pragma unroll
-    for (int r = 0; r < 8; r++) v[8 * e + r] = cmul(__ldg(Hp + 128 * (e + 2 * r)), v[8 * e + r]);
+    for (int r = 0; r < 8; r++) v[8 * e + r] = cmul(ldg_stream(Hp + 128 * (e + 2 * r)), v[8 * e + r]);
 }
 // transform output -> buffer in natural order: buf[t + 128j] = v[j], only the rows that hold kept samples (j >= jb)
 __device__ __forceinline__ void store16(const float2 (&v)[16], float2* __restrict__ buf, int jb) {
@@ -351,7 +398,8 @@ __device__ __noinline__ void fm_discriminate_blanked(const float2* __restrict__ 
 // (fm.c:86-160). Writes olen audio samples to aud[], updates sh.S[h] and the status row. The discriminator only sees
 // phase differences, so ph enters once: the carried state conj(last good sample) is kept in the true (rotated) domain
 // and moved into / out of this block's unrotated domain with one complex multiply each way.
-__device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, CtaShared& sh, const int olen, int h, int c, int b,
+template <class SH>
+__device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, const int olen, int h, int c, int b,
                                                 float ssq, float samp, float minsq, float2 ph,
                                                 float* __restrict__ aud) {
   const int t = threadIdx.x;
@@ -463,7 +511,8 @@ __device__ __noinline__ void fm_flat_output(const float* audA, const float* audB
 // Appendix B) so the kept-row tests fold away; 0 = take it from the launch arguments.
 template <int OLEN_T>
 __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(const ChanLaunch a) {
-  __shared__ CtaShared sh;
+  __shared__ FmShared<FM_ALIAS_AUX1 ? OLEN_T : 0> sh;
+  float* const aux1 = sh.audio_b();
   const int t = threadIdx.x;
   const int2 wk = a.work[blockIdx.x];
   if (t < 2) {
@@ -496,7 +545,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
       if (job < 2) {
         if (c < 0) {
 #pragma unroll 1
-          for (int o = t; o < olen; o += FFT2048_THREADS) sh.aux1[o] = 0.f;
+          for (int o = t; o < olen; o += FFT2048_THREADS) aux1[o] = 0.f;
           continue;
         }
         load_filtered16(v, X, a.N, (int)sh.P[h].bin, a.resp + (long long)c * NDEC);
@@ -517,11 +566,11 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
             const int ri = (ringbase + p) & (NDEC - 1);
             float za, zb;
             if (p < first) {
-              za = hist[0][ri];
-              zb = hist[1] ? hist[1][ri] : 0.f;
+              za = ldg_stream(hist[0] + ri);
+              zb = hist[1] ? ldg_stream(hist[1] + ri) : 0.f;
             } else {
               za = sh.aux0[p - first];
-              zb = sh.aux1[p - first];
+              zb = aux1[p - first];
               hist[0][ri] = za;
               if (hist[1]) hist[1][ri] = zb;
             }
@@ -534,7 +583,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
         const int e = sh.ephase[h];
         __syncthreads();  // every thread has read its stage-3 inputs; the buffer can take the output
         store16_stats(v, sh.buf, first, &ssq, &samp, &minsq);
-        fm_discriminate(a, sh, olen, h, c, b, ssq, samp, minsq, phase_from_index(a, e), h ? sh.aux1 : sh.aux0);
+        fm_discriminate(a, sh, olen, h, c, b, ssq, samp, minsq, phase_from_index(a, e), h ? aux1 : sh.aux0);
         if (t == 0) sh.ephase[h] = phase_advance(e, sh.P[h].phase_step, a.N);
       } else if (job == 2) {
         const float2* R = a.audio_resp + (long long)sh.P[0].audio_slot * NDEC + t;
@@ -560,7 +609,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
         }
       }
     }
-    if (!filtered) fm_flat_output(sh.aux0, sh.aux1, pcm_row + sh.P[0].pcm_off, wk.y >= 0 ? pcm_row + sh.P[1].pcm_off : nullptr, olen);
+    if (!filtered) fm_flat_output(sh.aux0, aux1, pcm_row + sh.P[0].pcm_off, wk.y >= 0 ? pcm_row + sh.P[1].pcm_off : nullptr, olen);
     __syncthreads();
   }
   if (t < 2) {
@@ -818,7 +867,9 @@ int launch_fm(const ChanLaunch& a, cudaStream_t st) {
   if (a.nwork <= 0) return 0;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(fm_kernel<960>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // 8 CTAs x (20.7 KB + 1 KB reserved) fit the 196 KB carve-out when channel B's audio is parked in the exchange buffer
+    cudaFuncSetAttribute(fm_kernel<960>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         FM_ALIAS_AUX1 ? 85 : (int)cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(fm_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
