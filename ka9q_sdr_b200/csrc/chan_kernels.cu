@@ -20,32 +20,9 @@ namespace k9 {
 
 // ---------------------------------------------------------------- common device helpers
 
-#ifndef FM_STREAM_LOADS
-#define FM_STREAM_LOADS 0
+#ifndef FM_CARVEOUT_PCT
+#define FM_CARVEOUT_PCT 70
 #endif
-#ifndef FM_ALIAS_AUX1
-#define FM_ALIAS_AUX1 1
-#endif
-// read-once streams (the per-channel response and audio history): keep them out of L1 so the spectrum windows that
-// neighbouring channels share and the twiddle / de-emphasis tables stay resident
-__device__ __forceinline__ float ldg_stream(const float* p) {
-#if FM_STREAM_LOADS
-  float r;
-  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");  // written by this CTA: not .nc
-  return r;
-#else
-  return *p;
-#endif
-}
-__device__ __forceinline__ float2 ldg_stream(const float2* p) {
-#if FM_STREAM_LOADS
-  float2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  return r;
-#else
-  return __ldg(p);
-#endif
-}
 
 struct CtaShared {
   float2 buf[NDEC];   // FFT exchange buffer; afterwards the olen kept samples y[0..olen)
@@ -59,24 +36,18 @@ struct CtaShared {
   ChanState S[2];
 };
 
-// FM pairs with the compile-time geometry (olen = 960): channel B's audio is parked in the part of the exchange buffer
-// that is idle between B's discriminator and the audio transform (bins [0, N_dec - olen) hold nothing then), which
-// brings 8 CTAs under the 196 KB carve-out and leaves ~60 KB of L1 for the shared twiddle / de-emphasis tables.
-template <int OLEN_T>
+// FM pairs keep no audio on chip: the discriminator appends its output straight to the channel's audio-history ring in
+// global memory (it has to land there anyway, fm.c:162 / filter.c:164), and the audio transform reads the whole 2048
+// sample window back from the ring (L1/L2 hits). 16.8 KB per CTA: 8 CTAs fit the 164 KB carve-out, which leaves
+// ~90 KB of L1 for the spectrum windows that neighbouring channels share and the twiddle / de-emphasis tables.
 struct FmShared {
-  float2 buf[NDEC];
-  float aux0[OLEN_T];
+  float2 buf[NDEC];  // FFT exchange buffer; afterwards the olen kept samples y[0..olen)
   float red[16];
   unsigned good[32];
   float scal[8];
-  int ephase[2];
+  int ephase[2];  // (k * block_start) mod N per channel of the work item
   ChanParams P[2];
   ChanState S[2];
-  __device__ __forceinline__ float* audio_b() { return reinterpret_cast<float*>(buf); }
-};
-template <>
-struct FmShared<0> : CtaShared {
-  __device__ __forceinline__ float* audio_b() { return aux1; }
 };
 
 // three block-wide reductions in one round trip. MODE 0: sum,sum,sum  1: sum,max,min  2: sum,sum,min
@@ -203,7 +174,7 @@ __device__ __forceinline__ void load_filtered16(float2 (&v)[16], const float2* _
 #pragma unroll
   for (int e = 0; e < 2; e++)
 #pragma unroll
-    for (int r = 0; r < 8; r++) v[8 * e + r] = cmul(ldg_stream(Hp + 128 * (e + 2 * r)), v[8 * e + r]);
+    for (int r = 0; r < 8; r++) v[8 * e + r] = cmul(__ldg(Hp + 128 * (e + 2 * r)), v[8 * e + r]);
 }
 // transform output -> buffer in natural order: buf[t + 128j] = v[j], only the rows that hold kept samples (j >= jb)
 __device__ __forceinline__ void store16(const float2 (&v)[16], float2* __restrict__ buf, int jb) {
@@ -333,7 +304,7 @@ __device__ __forceinline__ float fm_arg(float2 y, float2 st) {
 // some sample of the block is below the blanking threshold (fm.c:121,130,141). Builds the good-sample bitmap (one
 // ballot per 32 samples), then audio[n] = arg(y[src] * conj(y[prev good before src])), src = last good sample <= n.
 __device__ __noinline__ void fm_discriminate_blanked(const float2* __restrict__ ybuf, int olen, float min_ampl,
-                                                     float2 old_state, float old_last, float* __restrict__ aud,
+                                                     float2 old_state, float old_last, float* __restrict__ aud, int rb,
                                                      unsigned* good, float* scal, float* fsum_out, float* pos_out,
                                                      float* neg_out) {
   const int t = threadIdx.x;
@@ -379,7 +350,7 @@ __device__ __noinline__ void fm_discriminate_blanked(const float2* __restrict__ 
       }
       if (cj) st.y = -st.y;
       const float audio = have ? fm_arg(ys, st) : old_last;
-      aud[o] = audio;
+      aud[(rb + o) & (NDEC - 1)] = audio;
       fsum += audio;
       if (g && o > 0) {
         pos = fmaxf(pos, audio);
@@ -395,13 +366,13 @@ __device__ __noinline__ void fm_discriminate_blanked(const float2* __restrict__ 
 }
 
 // Squelch + discriminator for one channel-block whose kept samples (without the block's LO phase ph) are in sh.buf
-// (fm.c:86-160). Writes olen audio samples to aud[], updates sh.S[h] and the status row. The discriminator only sees
+// (fm.c:86-160). Appends olen audio samples to the ring aud[] at rb, updates sh.S[h] and the status row. The discriminator only sees
 // phase differences, so ph enters once: the carried state conj(last good sample) is kept in the true (rotated) domain
 // and moved into / out of this block's unrotated domain with one complex multiply each way.
 template <class SH>
 __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, const int olen, int h, int c, int b,
                                                 float ssq, float samp, float minsq, float2 ph,
-                                                float* __restrict__ aud) {
+                                                float* __restrict__ aud, int rb) {
   const int t = threadIdx.x;
   const float2* ybuf = sh.buf + (NDEC - olen);  // kept samples y[0..olen)
   block_reduce3<2>(ssq, samp, minsq, sh.red);
@@ -433,7 +404,7 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, con
       // blanking logic and every sample pays for it). audio[n] = arg(y[n] * conj(y[n-1])) (fm.c:130-132).
       {
         const float a0 = fm_arg(ybuf[t], t ? make_float2(ybuf[t - 1].x, -ybuf[t - 1].y) : old_state);
-        aud[t] = a0;
+        aud[(rb + t) & (NDEC - 1)] = a0;
         fsum = a0;
         if (t) {
           pos = a0;
@@ -446,14 +417,14 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, con
       for (int o = t + 128; o < olen; o += FFT2048_THREADS) {
         const float2 yp = ybuf[o - 1];
         const float audio = fm_arg(ybuf[o], make_float2(yp.x, -yp.y));
-        aud[o] = audio;
+        aud[(rb + o) & (NDEC - 1)] = audio;
         fsum += audio;
         pos = fmaxf(pos, audio);
         neg = fminf(neg, audio);
       }
-      if (t == ((olen - 1) & 127)) sh.scal[1] = aud[olen - 1];  // this thread wrote it
+      if (t == ((olen - 1) & 127)) sh.scal[1] = aud[(rb + olen - 1) & (NDEC - 1)];  // this thread wrote it
     } else {
-      fm_discriminate_blanked(ybuf, olen, min_ampl, old_state, old_last, aud, sh.good, sh.scal, &fsum, &pos, &neg);
+      fm_discriminate_blanked(ybuf, olen, min_ampl, old_state, old_last, aud, rb, sh.good, sh.scal, &fsum, &pos, &neg);
     }
     block_reduce3<1>(fsum, pos, neg, sh.red);
     const float init = sh.scal[0];
@@ -475,7 +446,7 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, con
   } else {
     // squelch closed (fm.c:155-160)
 #pragma unroll 1
-    for (int o = t; o < olen; o += FFT2048_THREADS) aud[o] = 0.f;
+    for (int o = t; o < olen; o += FFT2048_THREADS) aud[(rb + o) & (NDEC - 1)] = 0.f;
   }
   __syncthreads();  // all reads of sh.S[h], sh.scal and y are done
   if (t == 0) {
@@ -498,12 +469,13 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, con
 }
 
 // FLAT mode: the raw discriminator output goes out unfiltered and unscaled (fm.c:55,164-172). Cold, out of line.
-__device__ __noinline__ void fm_flat_output(const float* audA, const float* audB, int16_t* pa, int16_t* pb, int olen) {
+__device__ __noinline__ void fm_flat_output(const float* audA, const float* audB, int rb, int16_t* pa, int16_t* pb, int olen) {
   __syncthreads();
 #pragma unroll 1
   for (int o = threadIdx.x; o < olen; o += FFT2048_THREADS) {
-    pa[o] = scaleclip(audA[o]);
-    if (pb) pb[o] = scaleclip(audB[o]);
+    const int ri = (rb + o) & (NDEC - 1);
+    pa[o] = scaleclip(audA[ri]);
+    if (pb) pb[o] = scaleclip(audB[ri]);
   }
 }
 
@@ -511,8 +483,7 @@ __device__ __noinline__ void fm_flat_output(const float* audA, const float* audB
 // Appendix B) so the kept-row tests fold away; 0 = take it from the launch arguments.
 template <int OLEN_T>
 __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(const ChanLaunch a) {
-  __shared__ FmShared<FM_ALIAS_AUX1 ? OLEN_T : 0> sh;
-  float* const aux1 = sh.audio_b();
+  __shared__ FmShared sh;
   const int t = threadIdx.x;
   const int2 wk = a.work[blockIdx.x];
   if (t < 2) {
@@ -528,14 +499,19 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
   const int first = NDEC - olen;
   const int jb = first >> 7, rem = first & 127;
   const bool filtered = sh.P[0].audio_slot >= 0;
-  float* hist[2] = {a.audio_hist ? a.audio_hist + (long long)wk.x * NDEC : nullptr,
-                    (a.audio_hist && wk.y >= 0) ? a.audio_hist + (long long)wk.y * NDEC : nullptr};
+  // Audio-history rings of the pair (2048 floats each). An absent channel B reads the spare all-zero ring that follows
+  // the last channel's; nothing is ever written to it.
+  float* const histA = a.audio_hist + (long long)wk.x * NDEC;
+  float* const histB = a.audio_hist + (long long)(wk.y >= 0 ? wk.y : a.nchan_total) * NDEC;
   float2 v[16];
 
   for (int b = 0; b < a.nblocks; b++) {
     const long long m = a.block0 + b;
     const float2* X = a.spec + (long long)b * a.spec_stride;
     int16_t* pcm_row = a.pcm + (long long)b * a.pcm_stride;
+    // REAL overlap-save input of the post-detection filter, L=olen, M=NDEC-olen+1 (fm.c:39-43): the 2048-sample window
+    // of block m is ring[(ringbase + p) & 2047], p = 0..2047; its last olen entries are this block's new audio.
+    const int ringbase = (int)(((m + 1) * (long long)olen) & (NDEC - 1));
     // Four transforms per pair-block share ONE copy of the FFT code: job 0/1 = predetection filter of channel A/B,
     // job 2 = forward transform of the audio pair (as conj(IFFT(conj z))), job 3 = its inverse.
 #pragma unroll 1
@@ -543,38 +519,21 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
       const int h = job & 1;
       const int c = h ? wk.y : wk.x;
       if (job < 2) {
-        if (c < 0) {
-#pragma unroll 1
-          for (int o = t; o < olen; o += FFT2048_THREADS) aux1[o] = 0.f;
-          continue;
-        }
+        if (c < 0) continue;
         load_filtered16(v, X, a.N, (int)sh.P[h].bin, a.resp + (long long)c * NDEC);
       } else if (job == 2) {
         if (!filtered) break;
-        // REAL overlap-save input of the post-detection filter, L=olen, M=NDEC-olen+1 (fm.c:39-43): two real channels
-        // ride one complex transform, z = audA + j audB (the filter's impulse response is real). History lives in a
-        // 2048-sample ring per channel; this block's new samples are appended to it here.
-        const int ringbase = (int)(((m + 1) * (long long)olen) & (NDEC - 1));
-        // Straight into the transform's input registers: row j = e + 2r of thread t is sample p = t + 128j; history
-        // rows (p < first) come from the ring, the rest are this block's new samples, appended to the ring here.
-        // conj on the way in: forward transform via the backward code.
+        // Two real channels ride one complex transform, z = audA + j audB (the filter's impulse response is real),
+        // straight into the transform's input registers: row j = e + 2r of thread t is sample p = t + 128j. The
+        // discriminators appended this block's samples to the rings (global memory, made visible to the CTA by the
+        // barrier that ends fm_discriminate). conj on the way in: forward transform via the backward code.
+        const int r0 = (ringbase + t) & (NDEC - 1);
 #pragma unroll
         for (int e = 0; e < 2; e++)
 #pragma unroll
           for (int r = 0; r < 8; r++) {
-            const int p = t + 128 * (e + 2 * r);
-            const int ri = (ringbase + p) & (NDEC - 1);
-            float za, zb;
-            if (p < first) {
-              za = ldg_stream(hist[0] + ri);
-              zb = hist[1] ? ldg_stream(hist[1] + ri) : 0.f;
-            } else {
-              za = sh.aux0[p - first];
-              zb = aux1[p - first];
-              hist[0][ri] = za;
-              if (hist[1]) hist[1][ri] = zb;
-            }
-            v[8 * e + r] = make_float2(za, -zb);
+            const int ri = (r0 + 128 * (e + 2 * r)) & (NDEC - 1);
+            v[8 * e + r] = make_float2(histA[ri], -histB[ri]);
           }
       }
       fft2048<+1>(v, sh.buf, a.tw2048);
@@ -583,7 +542,8 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
         const int e = sh.ephase[h];
         __syncthreads();  // every thread has read its stage-3 inputs; the buffer can take the output
         store16_stats(v, sh.buf, first, &ssq, &samp, &minsq);
-        fm_discriminate(a, sh, olen, h, c, b, ssq, samp, minsq, phase_from_index(a, e), h ? aux1 : sh.aux0);
+        fm_discriminate(a, sh, olen, h, c, b, ssq, samp, minsq, phase_from_index(a, e), h ? histB : histA,
+                        (ringbase + first) & (NDEC - 1));
         if (t == 0) sh.ephase[h] = phase_advance(e, sh.P[h].phase_step, a.N);
       } else if (job == 2) {
         const float2* R = a.audio_resp + (long long)sh.P[0].audio_slot * NDEC + t;
@@ -609,7 +569,9 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
         }
       }
     }
-    if (!filtered) fm_flat_output(sh.aux0, aux1, pcm_row + sh.P[0].pcm_off, wk.y >= 0 ? pcm_row + sh.P[1].pcm_off : nullptr, olen);
+    if (!filtered)
+      fm_flat_output(histA, histB, (ringbase + first) & (NDEC - 1), pcm_row + sh.P[0].pcm_off,
+                     wk.y >= 0 ? pcm_row + sh.P[1].pcm_off : nullptr, olen);
     __syncthreads();
   }
   if (t < 2) {
@@ -867,10 +829,10 @@ int launch_fm(const ChanLaunch& a, cudaStream_t st) {
   if (a.nwork <= 0) return 0;
   static bool configured = false;
   if (!configured) {
-    // 8 CTAs x (20.7 KB + 1 KB reserved) fit the 196 KB carve-out when channel B's audio is parked in the exchange buffer
-    cudaFuncSetAttribute(fm_kernel<960>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         FM_ALIAS_AUX1 ? 85 : (int)cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(fm_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // 8 CTAs x (16.8 KB + 1 KB reserved) = 143 KB: ask for the 164 KB carve-out (percent of 228 KB, rounded up by the
+    // driver to the next supported size), the rest of the 256 KB stays L1
+    cudaFuncSetAttribute(fm_kernel<960>, cudaFuncAttributePreferredSharedMemoryCarveout, FM_CARVEOUT_PCT);
+    cudaFuncSetAttribute(fm_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, FM_CARVEOUT_PCT);
     configured = true;
   }
   if (a.olen == 960)

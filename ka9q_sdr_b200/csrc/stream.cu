@@ -441,8 +441,9 @@ int ka9q_stream_commit(ka9q_stream* s) {
   K9_CUDA(cudaMemcpy(s->d_params, s->h_params.data(), sizeof(ChanParams) * K, cudaMemcpyHostToDevice));
   K9_CUDA(cudaMemcpy(s->d_state, st.data(), sizeof(ChanState) * K, cudaMemcpyHostToDevice));
   if (any_fm) {
-    K9_CUDA(cudaMalloc(&s->d_audio_hist, sizeof(float) * (size_t)K * NDEC));
-    K9_CUDA(cudaMemset(s->d_audio_hist, 0, sizeof(float) * (size_t)K * NDEC));  // zero history (filter.c:87)
+    // one ring per channel + a spare all-zero ring that stands in for the missing partner of an unpaired FM channel
+    K9_CUDA(cudaMalloc(&s->d_audio_hist, sizeof(float) * (size_t)(K + 1) * NDEC));
+    K9_CUDA(cudaMemset(s->d_audio_hist, 0, sizeof(float) * (size_t)(K + 1) * NDEC));  // zero history (filter.c:87)
   }
   K9_CUDA(cudaMalloc(&s->d_pcm, sizeof(int16_t) * 2 * (size_t)B * s->pcm_stride));
   K9_CUDA(cudaMemset(s->d_pcm, 0, sizeof(int16_t) * 2 * (size_t)B * s->pcm_stride));
