@@ -20,6 +20,9 @@ namespace k9 {
 
 // ---------------------------------------------------------------- common device helpers
 
+#ifndef FM_FEWER_BARRIERS
+#define FM_FEWER_BARRIERS 1
+#endif
 #ifndef FM_CARVEOUT_PCT
 #define FM_CARVEOUT_PCT 70
 #endif
@@ -42,7 +45,7 @@ struct CtaShared {
 // ~90 KB of L1 for the spectrum windows that neighbouring channels share and the twiddle / de-emphasis tables.
 struct FmShared {
   float2 buf[NDEC];  // FFT exchange buffer; afterwards the olen kept samples y[0..olen)
-  float red[16];
+  float red[16], red2[16];  // one scratch row per reduction of a channel-block: no barrier needed to recycle them
   unsigned good[32];
   float scal[8];
   int ephase[2];  // (k * block_start) mod N per channel of the work item
@@ -51,12 +54,13 @@ struct FmShared {
 };
 
 // three block-wide reductions in one round trip. MODE 0: sum,sum,sum  1: sum,max,min  2: sum,sum,min
-template <int MODE>
+// PROTECT=false: the caller guarantees a barrier between the previous readers of red[] and this call.
+template <int MODE, bool PROTECT = true>
 __device__ __forceinline__ void block_reduce3(float& a, float& b, float& c, float* red) {
   a = warp_sum(a);
   b = MODE == 1 ? warp_max(b) : warp_sum(b);
   c = MODE == 0 ? warp_sum(c) : warp_min(c);
-  __syncthreads();  // protect red[] from the previous use
+  if (PROTECT) __syncthreads();  // protect red[] from the previous use
   const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
     red[w] = a;
@@ -375,7 +379,8 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, con
                                                 float* __restrict__ aud, int rb) {
   const int t = threadIdx.x;
   const float2* ybuf = sh.buf + (NDEC - olen);  // kept samples y[0..olen)
-  block_reduce3<2>(ssq, samp, minsq, sh.red);
+  // (its barrier also publishes the kept samples store16_stats just wrote; red[] was last read a barrier ago)
+  block_reduce3<2, !FM_FEWER_BARRIERS>(ssq, samp, minsq, sh.red);
   if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen, ph);
   const float bb_power = ssq / (2 * olen);
   const float avg_amp = samp / ((float)M_SQRT2 * olen);
@@ -413,7 +418,7 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, con
           sh.scal[0] = a0;
         }
       }
-#pragma unroll 2
+#pragma unroll 2  // (4 and 8 measured slower: code size)
       for (int o = t + 128; o < olen; o += FFT2048_THREADS) {
         const float2 yp = ybuf[o - 1];
         const float audio = fm_arg(ybuf[o], make_float2(yp.x, -yp.y));
@@ -426,7 +431,7 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, con
     } else {
       fm_discriminate_blanked(ybuf, olen, min_ampl, old_state, old_last, aud, rb, sh.good, sh.scal, &fsum, &pos, &neg);
     }
-    block_reduce3<1>(fsum, pos, neg, sh.red);
+    block_reduce3<1, !FM_FEWER_BARRIERS>(fsum, pos, neg, FM_FEWER_BARRIERS ? sh.red2 : sh.red);
     const float init = sh.scal[0];
     const float pdev_pos = fmaxf(pos, init);
     const float pdev_neg = fminf(neg, init);
@@ -536,7 +541,8 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
             v[8 * e + r] = make_float2(histA[ri], -histB[ri]);
           }
       }
-      fft2048<+1>(v, sh.buf, a.tw2048);
+      // the buffer's previous readers are a barrier behind us except after job 2 (its last stage just read it)
+      fft2048<+1>(v, sh.buf, a.tw2048, !FM_FEWER_BARRIERS || job == 3);
       if (job < 2) {
         float ssq, samp, minsq;
         const int e = sh.ephase[h];

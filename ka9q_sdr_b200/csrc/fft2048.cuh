@@ -38,7 +38,8 @@ __device__ __forceinline__ float2 tw_mul(float2 a, float wx, float wy) {
 }
 
 template <int SIGN>
-__device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb, const float2* __restrict__ tw) {
+__device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb, const float2* __restrict__ tw,
+                                        bool war_sync = true) {
   const int t = threadIdx.x;
   // ---- stage 1: two radix-8 butterflies, p = t + 128e; y1[8p + j] = w_2048^(p j) * DFT8 ----
 #pragma unroll
@@ -52,7 +53,7 @@ __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb
       v[8 * e + 2 * jj + 1] = tw_mul<SIGN>(v[8 * e + 2 * jj + 1], w.z, w.w);
     }
   }
-  __syncthreads();  // WAR: previous users of the buffer are done
+  if (war_sync) __syncthreads();  // WAR: previous users of the buffer are done (CTA-uniform flag)
   {
     // a = 8p + j, swizzled a ^ (t & 15): only the low nibble changes, so per j one XOR on a 3-bit value
     const int sw = t & 15;
