@@ -7,6 +7,7 @@
 #include "bigfft.cuh"
 #include "fft_regs.cuh"
 #include "util.cuh"
+#include "bigfft_r128.cuh"
 
 namespace k9 {
 
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(T*(R1 > R2 ? R1 : R2)) fft_pass_async_kernel(c
 #pragma unroll
         for (int j = 0; j < R1; j++) {
           float2 o = v[j];
-          if (j > 0 && pA > 0) o = cmul(o, __ldg(a.tw_r + pA * j));
+          if (j > 0) o = cmul(o, __ldg(a.tw_r + pA * j));  // tw_r[0] == 1 exactly: no test on pA
           sm[colA * S + R1 * pA + j] = o;
         }
       }
@@ -249,17 +250,22 @@ __global__ void __launch_bounds__(T*(R1 > R2 ? R1 : R2)) fft_pass_async_kernel(c
         const int qg = c % s;
         const int pg = c / s;
         float2* out = a.out + (long long)batch * a.out_batch_stride + qg + (long long)s * ((long long)R * pg);
-        const bool last = (a.n_cur == R);
+        if (a.n_cur != R) {
+          // inter-pass twiddles W_N^(pg*jt*s): all table loads are issued before the first product (no per-output
+          // branch: entry 0 of both tables is exactly 1, so e == 0 needs no special case)
+          const unsigned es = (unsigned)pg * (unsigned)s;
+          float2 lo[R2], hi[R2];
 #pragma unroll
-        for (int j = 0; j < R2; j++) {
-          const int jt = q + R1 * j;
-          float2 o = w[j];
-          if (!last) {
-            const unsigned e = (unsigned)pg * (unsigned)jt * (unsigned)s;  // < N
-            if (e != 0) o = cmul(o, big_twiddle<SIGN>(a, e));
+          for (int j = 0; j < R2; j++) {
+            const unsigned e = es * (unsigned)(q + R1 * j);  // < N
+            lo[j] = __ldg(a.tw_lo + (e & 1023u));
+            hi[j] = __ldg(a.tw_hi + (e >> 10));
           }
-          out[(long long)s * jt] = o;
+#pragma unroll
+          for (int j = 0; j < R2; j++) w[j] = cmul(w[j], cmul(lo[j], hi[j]));
         }
+#pragma unroll
+        for (int j = 0; j < R2; j++) out[(long long)s * (q + R1 * j)] = w[j];
       }
     }
     __syncthreads();  // the exchange buffer is reused by the next tile
@@ -526,7 +532,10 @@ int bigfft_exec(const BigFftPlan* plan, const BigFftIn& in, float2* out, long lo
     a.tw_lo = plan->tw_lo;
     a.tw_hi = plan->tw_hi;
     a.tw_r = plan->tw_r[p];
-    cudaError_t e = launch_pass_async(plan->R1[p], plan->R2[p], a, batch, sign, /*qfast=*/(N / n_cur) == 1, stream);
+    static const bool use128 = !(getenv("KA9Q_B200_FFT_R128") && atoi(getenv("KA9Q_B200_FFT_R128")) == 0);
+    cudaError_t e = use128 ? launch_pass128(plan->R1[p], plan->R2[p], a, batch, sign, stream) : cudaErrorNotSupported;
+    if (e == cudaErrorNotSupported)
+      e = launch_pass_async(plan->R1[p], plan->R2[p], a, batch, sign, /*qfast=*/(N / n_cur) == 1, stream);
     if (e == cudaErrorNotSupported)
       e = launch_pass(plan->R1[p], plan->R2[p], a, batch, sign, /*qfast=*/(N / n_cur) == 1, stream);
     if (e != cudaSuccess) {
