@@ -21,6 +21,9 @@
 
 namespace k9 {
 
+#ifndef P128_MIN_CTAS
+#define P128_MIN_CTAS 6
+#endif
 constexpr int P128_THREADS = 128;
 constexpr int P128_S = 129;  // padded column stride of the exchange buffer (float2): lanes = columns -> distinct banks
 
@@ -36,7 +39,7 @@ __device__ __forceinline__ float2 p128_twN(const PassArgs& a, unsigned e) {
 
 // ---- first pass: s == 1, n_cur == N. grid = (ncols/16, batch) ----
 template <bool RING_S16>
-__global__ void __launch_bounds__(P128_THREADS, 5) fft_pass128_first_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(P128_THREADS, P128_MIN_CTAS) fft_pass128_first_kernel(const PassArgs a) {
   __shared__ P128Shared sh;
   const int t = threadIdx.x;
   const int batch = blockIdx.y;
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(P128_THREADS, 5) fft_pass128_first_kernel(cons
 }
 
 // ---- middle pass: 1 < s, 16 | s, n_cur != 128. grid = (ncols/16, batch) ----
-__global__ void __launch_bounds__(P128_THREADS, 5) fft_pass128_mid_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(P128_THREADS, P128_MIN_CTAS) fft_pass128_mid_kernel(const PassArgs a) {
   __shared__ P128Shared sh;
   const int t = threadIdx.x;
   const int batch = blockIdx.y;
@@ -164,8 +167,54 @@ __global__ void __launch_bounds__(P128_THREADS, 5) fft_pass128_mid_kernel(const 
   }
 }
 
+// ---- last pass, R = 160 = 16 x 10 (no inter-pass twiddle, s = N/160, pg = 0): 160 threads, tile = 16 columns ----
+// stage A radix 16 (one butterfly per thread), stage B radix 10 (256 butterflies over 160 threads: two rounds, the
+// second 60 % full); lanes = 16 adjacent columns in both stages, so loads and stores are 128-byte rows.
+constexpr int P160_THREADS = 160;
+constexpr int P160_S = 161;
+__global__ void __launch_bounds__(P160_THREADS, 4) fft_pass160_last_kernel(const PassArgs a) {
+  __shared__ float2 u[16 * P160_S];
+  const int t = threadIdx.x;
+  const int batch = blockIdx.y;
+  const int col0 = blockIdx.x * 16;
+  const int ncols = a.ncols;  // == s
+  const int col = t & 15;
+  float2 v[16];
+  {
+    const int p = t >> 4;  // < 10: x[c + ncols*(p + 10r)], r < 16
+    const float2* in = reinterpret_cast<const float2*>(a.in) + (long long)batch * a.in_batch_stride + col0 + col;
+#pragma unroll
+    for (int r = 0; r < 16; r++) v[r] = __ldg(in + (long long)ncols * (p + 10 * r));
+    Dft<16, -1>::run(v);
+    float2* up = u + col * P160_S + 16 * p;
+    up[0] = v[0];
+#pragma unroll
+    for (int j = 1; j < 16; j++) up[j] = cmul(v[j], __ldg(a.tw_r + p * j));
+  }
+  __syncthreads();
+  float2* outb = a.out + (long long)batch * a.out_batch_stride + col0 + col;
+#pragma unroll
+  for (int round = 0; round < 2; round++) {
+    const int q = (t >> 4) + 10 * round;  // < 16: u[col][q + 16r], r < 10 -> jt = q + 16j
+    if (q < 16) {
+      const float2* up = u + col * P160_S + q;
+#pragma unroll
+      for (int r = 0; r < 10; r++) v[r] = up[16 * r];
+      Dft<10, -1>::run(v);
+      float2* o = outb + (long long)ncols * q;
+#pragma unroll
+      for (int j = 0; j < 10; j++) o[(long long)ncols * 16 * j] = v[j];
+    }
+  }
+}
+
 // returns cudaErrorNotSupported when the generic kernels should run this pass
 static cudaError_t launch_pass128(int R1, int R2, const PassArgs& a, int batch, int sign, cudaStream_t st) {
+  if (R1 == 10 && R2 == 16 && sign < 0 && a.n_cur == 160 && a.in_mode == IN_C32 && a.ncols % 16 == 0 &&
+      (long long)a.N < (1ll << 30)) {
+    fft_pass160_last_kernel<<<dim3(a.ncols / 16, batch), P160_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+  }
   if (!(R1 == 8 && R2 == 16) || sign >= 0 || a.n_cur == 128) return cudaErrorNotSupported;
   if (a.ncols % 16 != 0 || a.ring_cap >= (1ll << 30) || (long long)a.N >= (1ll << 30)) return cudaErrorNotSupported;
   const int s = a.N / a.n_cur;
