@@ -155,25 +155,40 @@ __device__ __forceinline__ void load16(float2 (&v)[16], const float2* __restrict
 __device__ __forceinline__ void load_filtered16(float2 (&v)[16], const float2* __restrict__ X, int N, int bin,
                                                 const float2* __restrict__ H) {
   const int t = threadIdx.x;
-  int i0 = bin + t;  // rows 0..7: positive frequencies
-  if (i0 < 0) i0 += N;
-  if (i0 >= N) i0 -= N;
-  int i1 = bin + t - 1024;  // rows 8..15: negative frequencies
-  if (i1 < 0) i1 += N;
-  if (i1 >= N) i1 -= N;
+  if (bin >= 1024 && bin + 1024 < N) {
+    // the whole window lies inside [0, N) (every channel but the few at the band edges; CTA-uniform): one base
+    // pointer, constant offsets. Row 8 of thread 0 is the Nyquist bin, which belongs to the positive side
+    // (filter.c:206: p <= N_dec/2).
+    const float2* p0 = X + bin + t;
+    const float2* pn = t ? p0 - 1024 : p0 + 1024;
 #pragma unroll
-  for (int e = 0; e < 2; e++)
+    for (int e = 0; e < 2; e++)
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int j = e + 2 * r;
-      int i = (j < 8 ? i0 : i1) + 128 * (j & 7);
-      if (i >= N) i -= N;
-      if (j == 8 && t == 0) {  // the Nyquist bin belongs to the positive side (filter.c:206: p <= N_dec/2)
-        i = bin + 1024;
-        if (i >= N) i -= N;
+      for (int r = 0; r < 8; r++) {
+        const int j = e + 2 * r;
+        v[8 * e + r] = __ldg(j < 8 ? p0 + 128 * j : (j == 8 ? pn : p0 + 128 * (j - 16)));
       }
-      v[8 * e + r] = __ldg(X + i);
-    }
+  } else {
+    int i0 = bin + t;  // rows 0..7: positive frequencies
+    if (i0 < 0) i0 += N;
+    if (i0 >= N) i0 -= N;
+    int i1 = bin + t - 1024;  // rows 8..15: negative frequencies
+    if (i1 < 0) i1 += N;
+    if (i1 >= N) i1 -= N;
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const int j = e + 2 * r;
+        int i = (j < 8 ? i0 : i1) + 128 * (j & 7);
+        if (i >= N) i -= N;
+        if (j == 8 && t == 0) {  // the Nyquist bin
+          i = bin + 1024;
+          if (i >= N) i -= N;
+        }
+        v[8 * e + r] = __ldg(X + i);
+      }
+  }
   const float2* Hp = H + t;
 #pragma unroll
   for (int e = 0; e < 2; e++)
