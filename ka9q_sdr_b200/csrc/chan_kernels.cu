@@ -660,12 +660,13 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
       if (c < 0) continue;
       const int bin = (int)a.params[c].bin;
       const bool isb = LINEAR && (a.params[c].flags & CH_ISB);
-      if (isb)
+      if (isb) {  // CTA-uniform; the mirror-bin fold is staged through shared memory
         stage_filtered<true>(X, a.N, bin, a.resp + (long long)c * NDEC, sh.buf);
-      else
-        stage_filtered<false>(X, a.N, bin, a.resp + (long long)c * NDEC, sh.buf);
-      __syncthreads();
-      load16(v, sh.buf);
+        __syncthreads();
+        load16(v, sh.buf);
+      } else {
+        load_filtered16(v, X, a.N, bin, a.resp + (long long)c * NDEC);  // straight into the transform's registers
+      }
       fft2048<+1>(v, sh.buf, a.tw2048);
       // amplitudes (am.c:56-58, linear.c:256-261) and block power straight from the registers
       float sig = 0.f, noi = 0.f, dummy = 0.f;
@@ -846,15 +847,17 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
 
 // ---------------------------------------------------------------- launchers
 
-int launch_fm(const ChanLaunch& a, cudaStream_t st) {
+int launch_fm(const ChanLaunch& a, cudaStream_t st, bool mixed) {
   if (a.nwork <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    // 8 CTAs x (16.8 KB + 1 KB reserved) = 143 KB: ask for the 164 KB carve-out (percent of 228 KB, rounded up by the
-    // driver to the next supported size), the rest of the 256 KB stays L1
-    cudaFuncSetAttribute(fm_kernel<960>, cudaFuncAttributePreferredSharedMemoryCarveout, FM_CARVEOUT_PCT);
-    cudaFuncSetAttribute(fm_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, FM_CARVEOUT_PCT);
-    configured = true;
+  // 8 CTAs x (16.8 KB + 1 KB reserved) = 143 KB: alone, ask for the 164 KB carve-out (percent of 228 KB, rounded up by
+  // the driver to the next supported size) and keep ~90 KB of L1 (measured: 228 -> 196 -> 164 KB = 0.528 -> 0.495 ->
+  // 0.491 ms per launch at cfg5); beside AM / linear kernels use their (maximum) carve-out so the CTAs can share SMs.
+  static int configured = -1;
+  const int pct = mixed ? (int)cudaSharedmemCarveoutMaxShared : FM_CARVEOUT_PCT;
+  if (configured != pct) {
+    cudaFuncSetAttribute(fm_kernel<960>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fm_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    configured = pct;
   }
   if (a.olen == 960)
     fm_kernel<960><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);

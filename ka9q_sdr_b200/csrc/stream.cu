@@ -643,7 +643,7 @@ static int issue_channels(ka9q_stream* s, int nblocks) {
     a.work = s->d_work_fm;
     a.nwork = s->n_fm;
     TimedRegion tr(s, TC_FM, s->s_comp);
-    K9_CHECK(launch_fm(a, s->s_comp) == 0, "fm kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    K9_CHECK(launch_fm(a, s->s_comp, s->n_am + s->n_lin > 0) == 0, "fm kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (s->n_am) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_am, 0));
   if (s->n_lin) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_lin, 0));
