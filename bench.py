@@ -219,13 +219,14 @@ def run_ours(args, plan):
     # synthetic input (rank 0 ingests the stream); pinned host buffers for the end-to-end leg
     nbytes_in = B * plan.L * 4
     pin_in = ch.PinnedBuffer(nbytes_in, np.int16)
-    if rank == 0 or args.mgpu == "allgather":
+    if rank == 0 or args.mgpu in ("allgather", "replicate"):
         pin_in.array[:] = make_input(plan, B)   # block-sharded FFT: every rank ingests the (int16) stream
     pin_pcm = [ch.PinnedBuffer(B * c.pcm_stride * 2, np.int16) for _ in range(2)]
     in_ptr = C.c_void_p(pin_in.ptr)
     pcm_ptrs = [C.c_void_p(p.ptr) for p in pin_pcm]
 
-    if multi:
+    replicate = multi and args.mgpu == "replicate"
+    if multi and not replicate:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(ch.nccl_unique_id()), dtype=torch.uint8))
@@ -252,7 +253,7 @@ def run_ours(args, plan):
             c.nccl_broadcast_spectrum(B, 0)
 
     def step_resident():
-        if not multi:
+        if not multi or replicate:
             c.compute_resident(B)
         else:
             spectrum_step()
@@ -267,11 +268,11 @@ def run_ours(args, plan):
         previous batch's copy-out (wait_fetch) before re-using that host buffer."""
         i = e2e_count[0]
         e2e_count[0] += 1
-        if not multi or rank == 0 or args.mgpu == "allgather":
+        if not multi or rank == 0 or args.mgpu in ("allgather", "replicate"):
             if i == 0:
                 c.push(in_ptr, B)      # prime: batch 0
             c.push(in_ptr, B)          # batch i+1 goes up while batch i is computed (the ring holds two batches)
-        if not multi:
+        if not multi or replicate:
             c.compute(B)
         else:
             # every rank returns its own PCM rows to the host
@@ -293,9 +294,18 @@ def run_ours(args, plan):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # nvidia-smi needs a few hundred ms to come up: every rank runs the same fixed number of extra untimed steps (the
-    # multi-GPU step contains a collective, so the count must not depend on the rank or on wall time)
-    for _ in range(args.warmup + 300):
+    # nvidia-smi needs a few hundred ms to come up, so ~1.2 s of untimed steps run first. The multi-GPU step contains a
+    # collective, so the count must be the same on every rank: it is derived from a step time agreed by all-reduce.
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        step_resident()
+    barrier()
+    est = torch.tensor([(time.perf_counter() - t0) / 20], dtype=torch.float64, device="cuda")
+    if multi:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)     # same count on every rank
+    n_extra = max(300, int(1.2 / max(float(est.item()), 1e-5)))   # ~1.2 s under load before the timed steps
+    for _ in range(args.warmup + n_extra):
         step_resident()
     barrier()
     c.timer_start()
@@ -339,7 +349,7 @@ def run_ours(args, plan):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = world * K * (B * plan.L / 1e6) / e2e_s
-    h2d = nbytes_in * (world if (multi and args.mgpu == "allgather") else 1)
+    h2d = nbytes_in * (world if (multi and args.mgpu in ("allgather", "replicate")) else 1)
     d2h = world * B * c.pcm_stride * 2
 
     if rank != 0:
@@ -398,9 +408,11 @@ def run_ours(args, plan):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": plan.name, "channels_per_gpu": K, "samprate": plan.samprate, "L": plan.L, "M": plan.M,
                    "N": plan.N, "decimate": plan.D, "blocks_per_step": B, "block_ms": 20,
-                   "parallelism": "1 GPU" if not multi else (
-                       f"channels x{world} (weak); forward FFT sharded by block + NCCL all-gather of spectra"
-                       if args.mgpu == "allgather" else f"channels x{world} (weak); NCCL spectrum broadcast from rank 0"),
+                   "parallelism": "1 GPU" if not multi else {
+                       "replicate": f"channels x{world} (weak); every rank ingests the int16 stream and runs its own "
+                                    "forward FFT, no data-path collective",
+                       "allgather": f"channels x{world} (weak); forward FFT sharded by block + NCCL all-gather of spectra",
+                       "broadcast": f"channels x{world} (weak); NCCL spectrum broadcast from rank 0"}[args.mgpu],
                    "l2": f"per-step working set {work_mb:.0f} MB > 126 MB L2 (responses+state+spectra+PCM); no flush needed"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -431,7 +443,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--ref-blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mgpu", default="allgather", choices=["allgather", "broadcast"])
+    ap.add_argument("--mgpu", default="replicate", choices=["replicate", "allgather", "broadcast"],
+                    help="multi-GPU spectrum distribution: replicate = every rank ingests the stream and runs its own "
+                         "forward FFT (no collective); allgather = FFT sharded by block + NCCL all-gather; broadcast = "
+                         "rank 0 transforms, NCCL broadcast")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     plan = make_plan(args.config, args.channels)
