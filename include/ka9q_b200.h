@@ -283,6 +283,61 @@ int ka9q_fft_plan_describe(int n, int *sizes);
  * `stages` x (15-tap half-band /2), highest rate first, separately per plane; state16 holds stages x hb15_state. */
 int ka9q_hb15_cascade(int device, int stages, struct hb15_state *states, const float *in, int n_in, float *out);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Wire-format glue either side of the path (host C, no GPU). What `radio` does between its sockets and
+ * the DSP: I/Q datagram -> sample stream with the reference's sequence / timestamp repair, and PCM rows -> RTP packets.
+ * The sockets themselves stay the caller's.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define KA9Q_RTP_MIN_SIZE 12  /* multicast.h:15 */
+#define KA9Q_IQ_PT 97         /* multicast.h:19: raw I/Q, 16 bit */
+#define KA9Q_IQ_PT8 98        /* multicast.h:20: raw I/Q, 8 bit */
+#define KA9Q_PCM_MONO_PT 11   /* multicast.h:22 */
+#define KA9Q_PCM_STEREO_PT 10 /* multicast.h:23 */
+#define KA9Q_PCM_BUFSIZE 480  /* audio.c:19: int16 words per PCM packet */
+
+/* struct rtp_state (multicast.h:41-50), same fields and order */
+typedef struct ka9q_rtp_state {
+  uint32_t ssrc;
+  int init;
+  uint16_t seq;
+  uint32_t timestamp;
+  long long packets;
+  long long bytes;
+  long long drops;
+  long long dupes;
+} ka9q_rtp_state;
+
+/* Receive side: replaces rtp_recv's parsing (main.c:313-344) and the packet head of proc_samples (radio.c:60-100). */
+typedef struct ka9q_ingest {
+  ka9q_rtp_state rtp; /* demod->input.rtp */
+  int iq_format;      /* KA9Q_IQ_S16 or KA9Q_IQ_S8: the stream's sample format; datagrams of the other type are ignored */
+  long long samples;  /* demod->input.samples: reset on SSRC change, counts zero-filled samples too */
+  long long zero_filled;
+  long long ignored;  /* too short, wrong payload type, duplicate, old, or a jump of more than 192000 samples */
+} ka9q_ingest;
+void ka9q_ingest_init(ka9q_ingest *g, int iq_format);
+/* One received UDP payload: RTP header (CSRCs, extension and padding handled as ntoh_rtp / main.c:322-326 do), the
+ * 24-byte legacy status header (main.c:340), then I/Q in host byte order. Appends to dst, in the stream's sample
+ * format, first `time_step` zero samples if the timestamp jumped (lost packets, radio.c:81-100) and then the payload.
+ * Returns the number of complex samples appended (>= 0), -1 if the datagram was ignored, -2 if dst has no room
+ * (`room` complex samples; the RTP state is then left untouched so the call can be repeated). */
+long long ka9q_ingest_datagram(ka9q_ingest *g, const void *datagram, int size, void *dst, long long room);
+/* rtp_process (multicast.c:305-340) on already-parsed header fields. */
+int ka9q_rtp_process(ka9q_rtp_state *state, uint32_t ssrc, uint16_t seq, uint32_t timestamp, int sampcnt);
+
+/* Send side: send_mono_output / send_stereo_output (audio.c:32-132) for PCM that is already int16 (the channel kernels
+ * apply scaleclip, audio.c:22-28). */
+typedef struct ka9q_pcm_out {
+  ka9q_rtp_state rtp; /* demod->output.rtp: ssrc, seq, timestamp, packets, bytes */
+  int silent;         /* demod->output.silent */
+} ka9q_pcm_out;
+typedef int (*ka9q_emit_fn)(void *user, const void *packet, int len); /* return < 0 to stop (send() failed) */
+/* Packetise `frames` frames of `channels` (1 or 2) interleaved host-order int16: chunks of at most 480 words, big
+ * endian, 12-byte RTP header (PT 11 mono / 10 stereo); an all-zero chunk is not sent but still advances the timestamp,
+ * and the first packet after silence carries the marker bit. Returns the number of packets emitted, -1 on bad
+ * arguments. */
+int ka9q_pcm_packetise(ka9q_pcm_out *out, const int16_t *pcm, int frames, int channels, ka9q_emit_fn emit, void *user);
+
 #ifdef __cplusplus
 }
 #endif

@@ -473,3 +473,92 @@ const char *ref_build_info(void) {
   return "verbatim reference sources from /root/reference, flags per reference Makefile:2 "
          "(-O3 -march=native -std=gnu11 -pthread -funsafe-math-optimizations -DNDEBUG=1)";
 }
+
+/* ---- wire-format glue: the reference's own functions around thin restatements of their callers ---- */
+#include <fcntl.h>
+#include <sys/socket.h>
+#include "multicast.h"
+
+/* One datagram through rtp_recv's parsing (main.c:313-344, real ntoh_rtp) and the packet head of proc_samples
+ * (radio.c:60-100, real rtp_process). Appends raw samples (4 or 2 bytes each, by payload type), zero bytes for lost
+ * samples. Returns complex samples appended, -1 if the datagram is ignored or dropped. */
+long long ref_glue_ingest(struct rtp_state *state, long long *samples, const unsigned char *datagram, int size,
+                          unsigned char *dst) {
+  if (size < RTP_MIN_SIZE) return -1;
+  unsigned char *content = malloc(size + 64);
+  memcpy(content, datagram, size);
+  struct rtp_header rtp;
+  memset(&rtp, 0, sizeof(rtp));
+  unsigned char *dp = ntoh_rtp(&rtp, content);
+  size -= (dp - content);
+  if (rtp.pad) {
+    size -= dp[size - 1];
+    rtp.pad = 0;
+  }
+  if (rtp.type != IQ_PT && rtp.type != IQ_PT8) {
+    free(content);
+    return -1;
+  }
+  dp += 24;
+  size -= 24;
+  const int bps = rtp.type == IQ_PT ? 4 : 2;
+  const int sampcount = size / bps;
+  if (rtp.ssrc != state->ssrc) *samples = 0;
+  const int time_step = rtp_process(state, &rtp, sampcount);
+  if (time_step < 0 || time_step > 192000) {
+    free(content);
+    return -1;
+  }
+  if (time_step > 0) {
+    *samples += time_step;
+    memset(dst, 0, (size_t)time_step * bps);
+    dst += (size_t)time_step * bps;
+  }
+  *samples += sampcount;
+  memcpy(dst, dp, (size_t)sampcount * bps);
+  free(content);
+  return (long long)time_step + sampcount;
+}
+
+/* The real send_mono_output / send_stereo_output (audio.c, compiled with renamed entry points: this harness owns the
+ * original names to capture PCM) writing into a UNIX datagram socket pair; the packets are read back verbatim.
+ * state5: ssrc, timestamp, seq, silent, (out) packets. Returns the number of packets, lens[i] their sizes,
+ * out = packets back to back. Keep calls short (a few packets): the socket queue is small. */
+/* Toolchain quirk of this image: with /opt/gcc, <complex.h> (pulled in by radio.h) resolves to libstdc++'s C wrapper whose
+ * c++config.h #undefs min/max, so audio.c's min() macro (misc.h:12) is gone by the time audio.c:44,:95 use it and the
+ * compiler emits a call to a function `min`. Both call sites pass ints. */
+#undef min
+int min(int a, int b) { return a < b ? a : b; }
+int refaudio_send_mono_output(struct demod *, const float *, int);
+int refaudio_send_stereo_output(struct demod *, const float *, int);
+int ref_glue_send(int channels, long long *state5, const float *buf, int frames, unsigned char *out, int out_cap,
+                  int *lens, int max_packets) {
+  int sv[2];
+  if (socketpair(AF_UNIX, SOCK_DGRAM, 0, sv) != 0) return -1;
+  fcntl(sv[1], F_SETFL, O_NONBLOCK);
+  struct demod *demod = calloc(1, sizeof(*demod));
+  demod->output.fd = sv[0];
+  demod->output.rtp.ssrc = (uint32_t)state5[0];
+  demod->output.rtp.timestamp = (uint32_t)state5[1];
+  demod->output.rtp.seq = (uint16_t)state5[2];
+  demod->output.silent = (int)state5[3];
+  if (channels == 2)
+    refaudio_send_stereo_output(demod, buf, frames);
+  else
+    refaudio_send_mono_output(demod, buf, frames);
+  int n = 0, used = 0;
+  while (n < max_packets) {
+    const int r = recv(sv[1], out + used, out_cap - used, 0);
+    if (r <= 0) break;
+    lens[n++] = r;
+    used += r;
+  }
+  state5[1] = demod->output.rtp.timestamp;
+  state5[2] = demod->output.rtp.seq;
+  state5[3] = demod->output.silent;
+  state5[4] = demod->output.rtp.packets;
+  close(sv[0]);
+  close(sv[1]);
+  free(demod);
+  return n;
+}

@@ -89,6 +89,9 @@ def lib():
                                  C.c_void_p]
     L.ref_filter_run.restype = C.c_int
     L.ref_osc_run.argtypes = [C.c_double, C.c_double, C.c_long, C.c_void_p]
+    L.ref_glue_ingest.restype = C.c_longlong
+    L.ref_glue_ingest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ref_glue_send.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.ref_hb15.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.ref_hb3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.ref_make_kaiser.argtypes = [C.c_void_p, C.c_uint, C.c_float]
@@ -285,3 +288,47 @@ def raw_irfft(X: np.ndarray, n: int) -> np.ndarray:
     lb.fftwf_execute(p)
     lb.fftwf_destroy_plan(p)
     return b
+
+
+# ---- wire-format glue ----
+class RtpState(C.Structure):
+    """struct rtp_state (multicast.h:41-50)"""
+    _fields_ = [("ssrc", C.c_uint32), ("init", C.c_int), ("seq", C.c_uint16), ("timestamp", C.c_uint32),
+                ("packets", C.c_longlong), ("bytes", C.c_longlong), ("drops", C.c_longlong), ("dupes", C.c_longlong)]
+
+
+class GlueIngest:
+    """rtp_recv parsing + proc_samples packet head, on the reference's own ntoh_rtp / rtp_process."""
+
+    def __init__(self):
+        self.state = RtpState()
+        self.samples = C.c_longlong(0)
+
+    def datagram(self, data: bytes):
+        """-> (ret, raw bytes appended): ret = complex samples appended, or -1 if ignored / dropped"""
+        buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+        out = np.zeros((192000 + 4096) * 4, dtype=np.uint8)
+        r = lib().ref_glue_ingest(C.byref(self.state), C.byref(self.samples), buf, len(data), _ptr(out))
+        if r < 0:
+            return r, b""
+        ptype = data[1] & 0x7F
+        return r, out[: r * (4 if ptype == 97 else 2)].tobytes()
+
+
+def glue_send(channels: int, state: dict, samples: np.ndarray):
+    """The real send_mono_output / send_stereo_output (audio.c:32-132) on float samples; returns the list of packets and
+    updates state {ssrc, timestamp, seq, silent, packets}. Call with a few packets' worth at a time."""
+    x = np.ascontiguousarray(samples, dtype=np.float32)
+    frames = x.size // channels
+    st = np.array([state["ssrc"], state["timestamp"], state["seq"], state["silent"], 0], dtype=np.int64)
+    out = np.zeros(64 * 2048, dtype=np.uint8)
+    lens = np.zeros(64, dtype=np.int32)
+    n = lib().ref_glue_send(channels, _ptr(st), _ptr(x), frames, _ptr(out), out.size, _ptr(lens), 64)
+    assert n >= 0
+    state.update(timestamp=int(st[1]) & 0xFFFFFFFF, seq=int(st[2]) & 0xFFFF, silent=int(st[3]),
+                 packets=state.get("packets", 0) + int(st[4]))
+    pk, off = [], 0
+    for i in range(n):
+        pk.append(out[off:off + lens[i]].tobytes())
+        off += int(lens[i])
+    return pk

@@ -20,6 +20,7 @@ REF = "/root/reference"
 def declared_symbols():
     txt = open(HEADER).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"typedef\s+[^;{]*\(\s*\*[^;]*;", "", txt)   # function-pointer typedefs declare no symbol
     names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", txt))
     names |= set(re.findall(r"extern\s+float\s+([A-Za-z_][A-Za-z0-9_]*)\s*;", txt))
     return {n for n in names if n not in ("defined",)}
