@@ -175,6 +175,31 @@ def test_long_run_against_reference(ref, mode):
         np.testing.assert_allclose(st["agc_gain"][5:, 0], r.status["agc_gain"][5:nb], rtol=2e-4)
 
 
+@pytest.mark.parametrize("L,M", [(4096, 4097), (3072, 5121)])
+def test_other_overlap_geometries_against_reference(ref, L, M):
+    """N/decimate stays 2048 but olen = L/4 is not the default 960 (1024 and 768): the run-time-olen kernels
+    (fm_kernel<0>, agc_kernel<..., 0>), another audio-filter length (AM = 2049 - olen, fm.c:39-43) and, for FM, one
+    paired and one unpaired channel."""
+    fs, D, N, nb = 192000, 4, 8192, 12
+    rng = np.random.default_rng(L)
+    n = nb * L
+    kf, kf2, ka, ku = 2048, -2304, -1024, 512
+    x = (synth.fm_carrier(n, fs, kf * fs / N, 1000.0, 3000.0, 0.2)
+         + synth.fm_carrier(n, fs, kf2 * fs / N, 700.0, 2500.0, 0.2)
+         + synth.am_carrier(n, fs, ka * fs / N, 1000.0, 0.5, 0.1)
+         + synth.ssb_two_tone(n, fs, ku * fs / N, [700.0, 1900.0], [0.05, 0.05])
+         + synth.awgn(rng, n, 0.01))
+    cfg = dict(samprate=fs, D=D, L=L, M=M, N=N, iq=synth._quantize(x))
+    chans = [("FM", kf, {}), ("AM", ka, {}), ("USB", ku, {}), ("FM", kf2, {}), ("FM", kf, {})]   # 3 FM: a pair + one
+    c, pcm, st, filt = run_gpu(cfg, chans, nb, max_blocks=5)
+    assert c.olen == L // D
+    for i, (mode, k, _) in enumerate(chans):
+        r = ref.chain_run(mode, fs, L, M, D, cfg["iq"], carrier_hz=k * fs / N, lo_cycles=-k / N, want_filt=mode != "USB")
+        check_pcm(mode, c.channel_pcm(pcm, i), r.pcm, L // D, label=f"{mode}@{k}")
+        if r.filt is not None:
+            assert rel_rms(filt[i], r.filt[:nb]) < FILT_TOL
+
+
 def test_fm_squelch_closes_on_noise_like_the_reference(ref):
     cfg = synth.cfg1_fm(12)
     rng = np.random.default_rng(9)
