@@ -852,12 +852,16 @@ int launch_fm(const ChanLaunch& a, cudaStream_t st, bool mixed) {
   // 8 CTAs x (16.8 KB + 1 KB reserved) = 143 KB: alone, ask for the 164 KB carve-out (percent of 228 KB, rounded up by
   // the driver to the next supported size) and keep ~90 KB of L1 (measured: 228 -> 196 -> 164 KB = 0.528 -> 0.495 ->
   // 0.491 ms per launch at cfg5); beside AM / linear kernels use their (maximum) carve-out so the CTAs can share SMs.
-  static int configured = -1;
+  // (function attributes are per device: one slot per device, so several GPUs driven from one process all get set up)
+  static int configured[64];
   const int pct = mixed ? (int)cudaSharedmemCarveoutMaxShared : FM_CARVEOUT_PCT;
-  if (configured != pct) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (configured[dev] != pct + 1000) {
     cudaFuncSetAttribute(fm_kernel<960>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(fm_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    configured = pct;
+    configured[dev] = pct + 1000;
   }
   if (a.olen == 960)
     fm_kernel<960><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
@@ -868,7 +872,10 @@ int launch_fm(const ChanLaunch& a, cudaStream_t st, bool mixed) {
 template <bool LINEAR, int G>
 static int launch_agc_g(const ChanLaunch& a, cudaStream_t st) {
   const size_t smem = sizeof(AgcShared<G>) + (LINEAR ? sizeof(float2) : sizeof(float)) * G * 1024;
-  static bool configured = false;
+  static bool configured_dev[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& configured = configured_dev[dev & 63];
   if (!configured) {
     cudaFuncSetAttribute(agc_kernel<LINEAR, G, 960>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(agc_kernel<LINEAR, G, 960>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
