@@ -170,9 +170,12 @@ __global__ void __launch_bounds__(P128_THREADS, P128_MIN_CTAS) fft_pass128_mid_k
 // ---- last pass, R = 160 = 16 x 10 (no inter-pass twiddle, s = N/160, pg = 0): 160 threads, tile = 16 columns ----
 // stage A radix 16 (one butterfly per thread), stage B radix 10 (256 butterflies over 160 threads: two rounds, the
 // second 60 % full); lanes = 16 adjacent columns in both stages, so loads and stores are 128-byte rows.
+#ifndef P160_MIN_CTAS
+#define P160_MIN_CTAS 4
+#endif
 constexpr int P160_THREADS = 160;
 constexpr int P160_S = 161;
-__global__ void __launch_bounds__(P160_THREADS, 4) fft_pass160_last_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(P160_THREADS, P160_MIN_CTAS) fft_pass160_last_kernel(const PassArgs a) {
   __shared__ float2 u[16 * P160_S];
   const int t = threadIdx.x;
   const int batch = blockIdx.y;
