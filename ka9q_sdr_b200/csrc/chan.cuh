@@ -80,6 +80,10 @@ struct ChanLaunch {
   // work list for this launch
   const int2* work;          // FM: (chanA, chanB or -1); AM / linear: (chan, -1)
   int nwork;
+  // AM / linear scratch between the front, recurrence and output kernels (rows indexed by block*nwork + work index)
+  float* agc_x;              // [nblocks*nwork][olen]: amplitude in; AM: (s - DC)*gain out, linear: gain out
+  float2* agc_y;             // [nblocks*nwork][olen]: kept filter output (linear only)
+  float* agc_pow;            // [nblocks*nwork][2]: block sums (am.c:56-58 / linear.c:256-261)
 };
 
 // mixed: AM / linear kernels of the same stream run beside this one (they need the maximum shared-memory carve-out; CTAs

@@ -12,6 +12,7 @@
 //   3. per-block LO phase factor exp(j*2*pi*((-k*(m*L-(M-1))) mod N)/N)       [Appendix C]
 //   4. demodulate + quantise                                               [fm.c / am.c / linear.c, audio.c:22-28]
 #include <math.h>
+#include <stdlib.h>
 #include "chan.cuh"
 #include "fft2048.cuh"
 #include "util.cuh"
@@ -606,20 +607,24 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
 // Both end in a strictly serial per-sample recurrence (hang AGC, and AM's carrier-DC tracker: am.c:60-74,
 // linear.c:269-280) that must keep the reference's operation order. One lane can only retire ~1 sample per 25 cycles, so
 // a CTA carries AGC_G channels: the parallel parts (response multiply, inverse FFT, amplitudes, quantisation) are done
-// channel after channel by all 128 threads, then lane 0 of warp g runs channel g's recurrence — AGC_G serial loops side
-// by side, each in its own warp so their branches never diverge against each other.
+// channel after channel by all 128 threads, then lane g of warp 0 runs channel g's recurrence — AGC_G serial loops in
+// lockstep in ONE warp (the recurrences are written with selects, so the lanes never diverge). One lane per warp, as
+// in the first version, costs a full issue slot per channel and instruction: ncu showed 610 M warp-instructions per
+// launch at 8192 AM channels, 70 % of them single-lane (profiles/r01_am_kernel_a.txt).
 
 // AGC_G channels per CTA (<= 4 = warps per CTA). Few channels: 1 per CTA minimises latency on a mostly idle GPU; many
 // channels: 4 per CTA amortises the serial phases and maximises throughput. The launcher picks.
 
+constexpr int AGC_ROW = 1024 + 1;  // floats per channel row: consecutive channels start one bank apart
+
 template <int AGC_G>
 struct AgcShared {
   float2 buf[NDEC];            // FFT exchange buffer
-  float amp[AGC_G][1024];      // amplitude (AM: envelope s[n])
-  float qg[AGC_G][1024];       // attack value headroom/x[n] precomputed in parallel; overwritten by gain[n]
+  float amp[AGC_G][AGC_ROW];   // amplitude (AM: envelope s[n]); rows padded: lane g reads row g in the serial loops
+  float qg[AGC_G][AGC_ROW];    // attack value headroom/x[n] precomputed in parallel; overwritten by gain[n]
   float red[16];
   float scal[4][4];
-  // dynamic tail: AM: dc[g][1024] floats; linear: kept samples y[g][1024] float2
+  // dynamic tail: AM: dc[g][AGC_ROW] floats; linear: kept samples y[g][1024] float2
 };
 
 template <bool LINEAR, int AGC_G, int OLEN_T>
@@ -627,9 +632,8 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
   extern __shared__ __align__(16) unsigned char smraw[];
   AgcShared<AGC_G>& sh = *reinterpret_cast<AgcShared<AGC_G>*>(smraw);
   float2* ykeep = reinterpret_cast<float2*>(smraw + sizeof(AgcShared<AGC_G>));  // [AGC_G][1024], LINEAR only
-  float* dcv = reinterpret_cast<float*>(smraw + sizeof(AgcShared<AGC_G>));      // [AGC_G][1024], AM only
+  float* dcv = reinterpret_cast<float*>(smraw + sizeof(AgcShared<AGC_G>));      // [AGC_G][AGC_ROW], AM only
   const int t = threadIdx.x;
-  const int warp = t >> 5;
   const int olen = OLEN_T ? OLEN_T : a.olen;
   const int first = NDEC - olen;
   const int jb = first >> 7, rem = first & 127;
@@ -639,8 +643,9 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
     const int w = blockIdx.x * AGC_G + g;
     chan[g] = w < a.nwork ? a.work[w].x : -1;
   }
-  // the warp that owns channel g keeps its parameters, state and LO phase index in registers
-  const int myc = warp < AGC_G ? chan[warp < AGC_G ? warp : 0] : -1;
+  // thread g < AGC_G owns channel g: its parameters, state and LO phase index stay in that thread's registers
+  const int myw = blockIdx.x * AGC_G + t;
+  const int myc = (t < AGC_G && myw < a.nwork) ? a.work[myw].x : -1;
   ChanParams P;
   ChanState S;
   int eph = 0;
@@ -708,9 +713,9 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
     //     the AGC state, so all threads compute those IEEE divisions in parallel. (3) The gain/hang recurrence itself
     //     (am.c:62-73, linear.c:269-279) is then compare + select per sample, same operands and order as the reference.
     if (!LINEAR) {
-      if ((t & 31) == 0 && myc >= 0) {
-        const float* am = sh.amp[warp];
-        float* dco = dcv + warp * 1024;
+      if (myc >= 0) {
+        const float* am = sh.amp[t];
+        float* dco = dcv + t * AGC_ROW;
         float dc = S.am_dc;
         // explicit batches of 8: all loads first, the FADD+FFMA chain, then the stores (the arrays could alias for
         // the compiler, which otherwise serialises every load behind the previous store)
@@ -739,13 +744,13 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
     for (int g = 0; g < AGC_G; g++) {
       if (chan[g] < 0) continue;
       const float headroom = a.params[chan[g]].headroom;
-      const float* xs = LINEAR ? sh.amp[g] : dcv + g * 1024;
+      const float* xs = LINEAR ? sh.amp[g] : dcv + g * AGC_ROW;
       for (int o = t; o < olen; o += FFT2048_THREADS) sh.qg[g][o] = headroom / xs[o];
     }
     __syncthreads();
-    if ((t & 31) == 0 && myc >= 0) {
-      const float* xs = LINEAR ? sh.amp[warp] : dcv + warp * 1024;
-      float* qg = sh.qg[warp];
+    if (myc >= 0) {
+      const float* xs = LINEAR ? sh.amp[t] : dcv + t * AGC_ROW;
+      float* qg = sh.qg[t];
       float gain = S.agc_gain;
       int hang = S.hang;
       const float headroom = P.headroom, rf = P.recovery_factor;
@@ -776,7 +781,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
       S.agc_gain = gain;
       S.hang = hang;
       ChanStatus st;
-      const float sig = sh.scal[warp][0], noi = sh.scal[warp][1];
+      const float sig = sh.scal[t][0], noi = sh.scal[t][1];
       st.bb_power = (sig + noi) / (2 * olen);  // am.c:78, linear.c:302
       st.snr = NAN;                            // linear.c:309 (no PLL)
       st.foffset = 0.f;
@@ -789,11 +794,11 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
     }
     __syncthreads();
     // ---- parallel output: gain / shift / quantise (linear.c:280-299, am.c:74, audio.c:22-28) ----
-    // every warp's lane 0 holds its channel's phase index; publish the per-channel scalars the output loop needs
-    if ((t & 31) == 0 && myc >= 0 && LINEAR) {
+    // the owner threads hold the channels' phase indices; publish the per-channel scalars the output loop needs
+    if (myc >= 0 && LINEAR) {
       const float2 ph = phase_from_index(a, eph);
-      sh.scal[warp][2] = ph.x;
-      sh.scal[warp][3] = ph.y;
+      sh.scal[t][2] = ph.x;
+      sh.scal[t][3] = ph.y;
     }
     if (LINEAR) __syncthreads();
 #pragma unroll 1
@@ -802,7 +807,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
       if (c < 0) continue;
       int16_t* pcm_row = a.pcm + (long long)b * a.pcm_stride + a.params[c].pcm_off;
       if (!LINEAR) {
-        const float* dcg = dcv + g * 1024;
+        const float* dcg = dcv + g * AGC_ROW;
         for (int o = t; o < olen; o += FFT2048_THREADS)
           pcm_row[o] = scaleclip((sh.amp[g][o] - dcg[o]) * sh.qg[g][o]);  // am.c:74
       } else {
@@ -836,12 +841,377 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
     if (myc >= 0) eph = phase_advance(eph, P.phase_step, a.N);
     __syncthreads();
   }
-  if ((t & 31) == 0 && myc >= 0) {
+  if (myc >= 0) {
     if (LINEAR && P.shift_cycles != 0.0) {
       double ph = S.shift_phase + P.shift_cycles * (double)olen * a.nblocks;
       S.shift_phase = ph - floor(ph);
     }
     a.state[myc] = S;
+  }
+}
+
+
+// ---------------------------------------------------------------- AM / linear, split form (the default)
+//
+// The fused agc_kernel above keeps a whole CTA (and its 49-65 KB of shared memory) waiting while one warp walks the
+// serial recurrences: at 8192 channels ncu shows 25 % issue utilisation, 12 resident warps per SM and the barrier as the
+// top stall (profiles/r01_am_kernel_b.txt). The split form gives each part the shape it wants:
+//   agc_front_kernel   one CTA per channel, like the FM predetection job: window x response -> 2048-point inverse FFT ->
+//                      amplitudes (and, for linear, the kept samples) straight from registers to a global scratch row
+//   agc_serial_kernel  one LANE per channel, 32 channels per warp in lockstep (the recurrences are select-based): tiles of
+//                      32 samples are transposed through shared memory so every global access is a 128-byte row; the
+//                      next tile is prefetched into registers while the current one is walked
+//   agc_output_kernel  (linear) one CTA per channel: gain / LO phase / shift oscillator / scaleclip, fully parallel; AM's
+//                      (s - DC) * gain -> scaleclip is cheap enough to ride the recurrence kernel's store stage
+// Same operations in the same order per channel as the fused kernel (bit-identical PCM), which stays selectable with
+// KA9Q_B200_AGC_FUSED=1.
+
+struct FrontShared {
+  float2 buf[NDEC];
+  float red[16];
+};
+
+template <bool LINEAR, int OLEN_T>
+__global__ void __launch_bounds__(FFT2048_THREADS, 8) agc_front_kernel(const ChanLaunch a) {
+  __shared__ FrontShared sh;
+  const int t = threadIdx.x;
+  const int w = blockIdx.x;
+  const int c = a.work[w].x;
+  const int olen = OLEN_T ? OLEN_T : a.olen;
+  const int first = NDEC - olen;
+  const int jb = first >> 7, rem = first & 127;
+  const int bin = (int)a.params[c].bin;
+  const bool isb = LINEAR && (a.params[c].flags & CH_ISB);
+  const float2* H = a.resp + (long long)c * NDEC;
+  float2 v[16];
+#pragma unroll 1
+  for (int b = 0; b < a.nblocks; b++) {
+    const float2* X = a.spec + (long long)b * a.spec_stride;
+    if (isb) {  // CTA-uniform; the mirror-bin fold is staged through shared memory
+      stage_filtered<true>(X, a.N, bin, H, sh.buf);
+      __syncthreads();
+      load16(v, sh.buf);
+    } else {
+      load_filtered16(v, X, a.N, bin, H);
+    }
+    fft2048<+1>(v, sh.buf, a.tw2048);
+    // amplitudes (am.c:56-58, linear.c:256-261) and block power straight from the registers
+    const long long row = (long long)b * a.nwork + w;
+    float* xr = a.agc_x + row * olen + (t - first);  // kept-sample index of row j is t - first + 128 j
+    float2* yr = LINEAR ? a.agc_y + row * olen + (t - first) : nullptr;
+    float sig = 0.f, noi = 0.f, dummy = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      if (j >= jb) {  // warp-uniform
+        if ((j > jb) || (t >= rem)) {
+          const float rp = v[j].x * v[j].x, ip = v[j].y * v[j].y;
+          sig += rp;
+          noi += ip;
+          xr[128 * j] = sqrtf(rp + ip);
+          if (LINEAR) yr[128 * j] = v[j];
+        }
+      }
+    }
+    if (a.filt_dbg) {
+      __syncthreads();
+      store16(v, sh.buf, jb);
+      __syncthreads();
+      const int e0 = phase_index0(a.params[c].bin, a.start0, a.N);
+      int e = e0;
+      for (int i = 0; i < b; i++) e = phase_advance(e, a.params[c].phase_step, a.N);
+      dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, sh.buf + first, olen,
+                         phase_from_index(a, e));
+    }
+    block_reduce3<0>(sig, noi, dummy, sh.red);  // also orders the exchange buffer for the next block
+    if (t == 0) {
+      a.agc_pow[2 * row] = sig;
+      a.agc_pow[2 * row + 1] = noi;
+    }
+  }
+}
+
+// One LANE per channel, 32 channels per CTA, and the per-sample work software-pipelined over five warps so that no
+// warp carries more than one short dependent chain or ~400 instructions per tile (a single warp doing everything needs
+// ~41 instructions and 131 cycles per sample: measured 0.27 ms per 4 blocks however few channels there are). Tiles of
+// 32 samples x 32 channels move through five stages, one barrier per step, four buffers deep:
+//   warp 0 (load)   tile s  : 32 coalesced 128-byte rows (prefetched one step ahead into registers) -> shared, transposed
+//   warp 1 (dc)     tile s-1: AM carrier-DC tracker (am.c:60): FADD + FFMA chain                       [AM only]
+//   warp 2 (div)    tile s-2: attack values headroom / x (IEEE division), which do not depend on the AGC state
+//   warp 3 (agc)    tile s-3: the gain / hang recurrence (am.c:62-73, linear.c:269-279), compare + select only
+//   warp 4 (store)  tile s-4: AM: (s - DC) * gain -> scaleclip -> int16 PCM rows; linear: gain rows back to the scratch
+// grid = ceil(nwork / 32).
+constexpr int SER_TP = 33;       // padded tile row (floats)
+constexpr int SER_THREADS = 160;
+struct SerialShared {
+  float x[4][32 * SER_TP];  // amplitude tiles [channel][sample]
+  float q[4][32 * SER_TP];  // headroom / x, overwritten by the result (linear: gain; AM: (s - DC) * gain)
+  float d[4][32 * SER_TP];  // AM: carrier level DC[n] (what the AGC follows)
+  float o[4][32 * SER_TP];  // AM: s - DC
+  int pcm_off[32];
+};
+
+template <bool LINEAR>
+__global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunch a) {
+  extern __shared__ __align__(16) unsigned char ser_raw[];
+  SerialShared& sh = *reinterpret_cast<SerialShared*>(ser_raw);
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const int w0 = blockIdx.x * 32;
+  const int nrows = min(32, a.nwork - w0);
+  const int w = w0 + lane;
+  const int c = lane < nrows ? a.work[w].x : -1;
+  const int olen = a.olen;
+  const int tpb = (olen + 31) >> 5;  // tiles per block
+  const int ntiles = tpb * a.nblocks;
+  // per-lane channel state, each field advanced (and finally stored) by one warp only
+  float gain = 1.f, dc = 0.f, headroom = 1.f, rf = 1.f;
+  int hang = 0, hangmax = 0;
+  if (c >= 0) {
+    const ChanParams& P = a.params[c];
+    const ChanState& S = a.state[c];
+    gain = S.agc_gain;
+    hang = S.hang;
+    dc = S.am_dc;
+    headroom = P.headroom;
+    rf = P.recovery_factor;
+    hangmax = P.hangmax;
+    if (role == 0) sh.pcm_off[lane] = P.pcm_off;
+  } else if (role == 0) {
+    sh.pcm_off[lane] = 0;
+  }
+  float nx[32];
+  // rows of tile T in the scratch: this lane's column of row r is tile_ptr(T) + r*olen
+  auto tile_ptr = [&](int T, int* cnt) -> float* {
+    const int b = T / tpb, k = T - b * tpb;
+    *cnt = min(32, olen - 32 * k);
+    return a.agc_x + ((long long)b * a.nwork + w0) * olen + 32 * k + lane;
+  };
+  auto fetch_tile = [&](int T) {
+    int cnt;
+    const float* g = tile_ptr(T, &cnt);
+    if (nrows == 32 && cnt == 32) {  // the usual case: no edge tests
+#pragma unroll
+      for (int r = 0; r < 32; r++) {
+        nx[r] = *g;
+        g += olen;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 32; r++) nx[r] = (r < nrows && lane < cnt) ? g[(long long)r * olen] : 1.f;
+    }
+  };
+  if (role == 0 && ntiles > 0) fetch_tile(0);
+  __syncthreads();
+#pragma unroll 1
+  for (int s = 0; s < ntiles + 4; s++) {
+    const int T = s - role;  // the tile this warp works on in this step
+    const bool live = T >= 0 && T < ntiles;
+    const int k = live ? T % tpb : 0;
+    const int cnt = min(32, olen - 32 * k);
+    const int bi = T & 3;
+    if (role == 0) {
+      if (live) {
+        float* xt = sh.x[bi];
+#pragma unroll
+        for (int r = 0; r < 32; r++) xt[r * SER_TP + lane] = nx[r];
+        if (T + 1 < ntiles) fetch_tile(T + 1);  // next tile's rows in flight during this step
+      }
+    } else if (role == 1) {
+      if (live && !LINEAR) {
+        const float* xt = sh.x[bi] + lane * SER_TP;
+        float* dt = sh.d[bi] + lane * SER_TP;
+        float* ot = sh.o[bi] + lane * SER_TP;
+        int i0 = 0;
+#pragma unroll 1
+        for (; i0 + 8 <= cnt; i0 += 8) {  // batches of 8: loads, chain, stores
+          float x[8], dd[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) x[i] = xt[i0 + i];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            dc += 0.0001f * (x[i] - dc);  // am.c:60
+            dd[i] = dc;                   // the AGC follows the carrier level (am.c:62)
+            x[i] = x[i] - dc;             // s - DC (am.c:74)
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            dt[i0 + i] = dd[i];
+            ot[i0 + i] = x[i];
+          }
+        }
+#pragma unroll 1
+        for (; i0 < cnt; i0++) {  // olen not a multiple of 8
+          const float x = xt[i0];
+          dc += 0.0001f * (x - dc);
+          dt[i0] = dc;
+          ot[i0] = x - dc;
+        }
+      }
+    } else if (role == 2) {
+      if (live) {
+        const float* xt = (LINEAR ? sh.x[bi] : sh.d[bi]) + lane * SER_TP;
+        float* qt = sh.q[bi] + lane * SER_TP;
+        int i0 = 0;
+#pragma unroll 1
+        for (; i0 + 8 <= cnt; i0 += 8) {
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) x[i] = xt[i0 + i];
+#pragma unroll
+          for (int i = 0; i < 8; i++) x[i] = headroom / x[i];
+#pragma unroll
+          for (int i = 0; i < 8; i++) qt[i0 + i] = x[i];
+        }
+#pragma unroll 1
+        for (; i0 < cnt; i0++) qt[i0] = headroom / xt[i0];
+      }
+    } else if (role == 3) {
+      if (live) {
+        const int b = T / tpb;
+        const float* xt = (LINEAR ? sh.x[bi] : sh.d[bi]) + lane * SER_TP;
+        const float* ot = sh.o[bi] + lane * SER_TP;
+        float* qt = sh.q[bi] + lane * SER_TP;
+        // am.c:62-73 / linear.c:269-279, same operands and order as the reference, written with selects. The start-up
+        // test (gain still NaN: am.c:64, linear.c:269) is hoisted out: a gain that is a number stays one.
+        const bool any_startup = __any_sync(0xffffffffu, isnan(gain));
+        auto agc_step_general = [&](float x, float q) {
+          const bool startup = isnan(gain);                     // gain = headroom/x, hang untouched
+          const bool over = !startup && (x * gain > headroom);  // attack: gain = headroom/x, hang = hangmax
+          const bool hold = !startup && !over && hang != 0;
+          const float grown = gain * rf;
+          gain = (startup || over) ? q : (hold ? gain : grown);
+          hang = over ? hangmax : (hold ? hang - 1 : hang);
+          return gain;
+        };
+        auto agc_step = [&](float x, float q) {
+          const bool over = x * gain > headroom;
+          const float kept = hang != 0 ? gain : gain * rf;  // hold, or recover
+          gain = over ? q : kept;
+          hang = over ? hangmax : max(hang - 1, 0);
+          return gain;
+        };
+        int i0 = 0;
+        if (!any_startup) {
+#pragma unroll 1
+          for (; i0 + 8 <= cnt; i0 += 8) {
+            float x[8], q[8], o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              x[i] = xt[i0 + i];
+              q[i] = qt[i0 + i];
+              o[i] = LINEAR ? 0.f : ot[i0 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) q[i] = agc_step(x[i], q[i]);
+#pragma unroll
+            for (int i = 0; i < 8; i++) qt[i0 + i] = LINEAR ? q[i] : o[i] * q[i];
+          }
+        }
+#pragma unroll 1
+        for (; i0 < cnt; i0++) {  // the stream's first tile, or olen not a multiple of 8
+          const float gn = agc_step_general(xt[i0], qt[i0]);
+          qt[i0] = LINEAR ? gn : ot[i0] * gn;
+        }
+        if (k == tpb - 1 && c >= 0) {  // end of block b: status row (the DC of the block's last sample is in the tile)
+          const long long row = (long long)b * a.nwork + w;
+          const float sig = a.agc_pow[2 * row], noi = a.agc_pow[2 * row + 1];
+          ChanStatus st;
+          st.bb_power = (sig + noi) / (2 * olen);  // am.c:78, linear.c:302
+          st.snr = NAN;                            // linear.c:309 (no PLL)
+          st.foffset = 0.f;
+          st.pdeviation = 0.f;
+          st.agc_gain = gain;
+          st.squelch_open = 1;
+          st.reserved[0] = LINEAR ? sig : xt[cnt - 1];
+          st.reserved[1] = LINEAR ? noi : 0.f;
+          a.status[(long long)b * a.nchan_total + c] = st;
+        }
+      }
+    } else {
+      if (live) {
+        const int b = T / tpb;
+        const float* qt = sh.q[bi] + lane;
+        if (LINEAR) {
+          int dummy;
+          float* g = tile_ptr(T, &dummy);
+#pragma unroll 8
+          for (int r = 0; r < nrows; r++)
+            if (lane < cnt) g[(long long)r * olen] = qt[r * SER_TP];
+        } else {
+          // am.c:74 + audio.c:22-28: row r is channel w0 + r
+          int16_t* pcm_blk = a.pcm + (long long)b * a.pcm_stride + 32 * k + lane;
+#pragma unroll 8
+          for (int r = 0; r < nrows; r++)
+            if (lane < cnt) pcm_blk[sh.pcm_off[r]] = scaleclip(qt[r * SER_TP]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (c >= 0) {
+    // every field is written by the warp that advanced it (the output kernel advances the shift oscillator)
+    if (role == 1 && !LINEAR) a.state[c].am_dc = dc;
+    if (role == 3) {
+      a.state[c].agc_gain = gain;
+      a.state[c].hang = hang;
+    }
+  }
+}
+
+// parallel output: gain / shift / quantise (linear.c:280-299, am.c:74, audio.c:22-28); one CTA per channel
+template <bool LINEAR>
+__global__ void __launch_bounds__(FFT2048_THREADS) agc_output_kernel(const ChanLaunch a) {
+  const int t = threadIdx.x;
+  const int w = blockIdx.x;
+  const int c = a.work[w].x;
+  const int olen = a.olen;
+  const ChanParams& P = a.params[c];
+  const int pcm_off = P.pcm_off;
+  const double shift_cycles = LINEAR ? P.shift_cycles : 0.0;
+  const bool shifted = shift_cycles != 0.0;
+  const double shift_phase = shifted ? a.state[c].shift_phase : 0.0;
+  const int nch = P.channels;
+  int e = LINEAR ? phase_index0(P.bin, a.start0, a.N) : 0;
+  const int phase_step = P.phase_step;
+#pragma unroll 1
+  for (int b = 0; b < a.nblocks; b++) {
+    const long long row = (long long)b * a.nwork + w;
+    const float* g = a.agc_x + row * olen;
+    int16_t* pcm_row = a.pcm + (long long)b * a.pcm_stride + pcm_off;
+    if (!LINEAR) {
+      for (int o = t; o < olen; o += FFT2048_THREADS) pcm_row[o] = scaleclip(g[o]);  // am.c:74
+    } else {
+      const float2* yk = a.agc_y + row * olen;
+      const float2 ph = phase_from_index(a, e);
+      const double phase0 = shifted ? shift_phase + shift_cycles * (double)olen * b : 0.0;
+      for (int o = t; o < olen; o += FFT2048_THREADS) {
+        const float gn = g[o];
+        const float2 y = cmul(yk[o], ph);            // the block's LO phase rides the gain multiply
+        float2 z = make_float2(y.x * gn, y.y * gn);  // linear.c:280
+        if (shifted) {
+          // post-detection shift oscillator (linear.c:283-289, osc.c:39-51): phasor(n) = exp(j*2*pi*f*n), n counted
+          // from the first sample the oscillator was stepped on
+          double p = phase0 + shift_cycles * (double)o;
+          p -= floor(p);
+          double sn, cs;
+          sincospi(2.0 * p, &sn, &cs);
+          z = cmul(z, make_float2((float)cs, (float)sn));
+        }
+        if (nch == 1) {
+          pcm_row[o] = scaleclip(z.x);  // linear.c:291-296
+        } else {
+          pcm_row[2 * o] = scaleclip(z.x);  // I left, Q right (linear.c:299)
+          pcm_row[2 * o + 1] = scaleclip(z.y);
+        }
+      }
+      e = phase_advance(e, phase_step, a.N);
+    }
+  }
+  if (LINEAR && shifted) {
+    __syncthreads();  // every thread has read the starting phase
+    if (t == 0) {
+      const double ph = shift_phase + shift_cycles * (double)olen * a.nblocks;
+      a.state[c].shift_phase = ph - floor(ph);
+    }
   }
 }
 
@@ -871,7 +1241,7 @@ int launch_fm(const ChanLaunch& a, cudaStream_t st, bool mixed) {
 }
 template <bool LINEAR, int G>
 static int launch_agc_g(const ChanLaunch& a, cudaStream_t st) {
-  const size_t smem = sizeof(AgcShared<G>) + (LINEAR ? sizeof(float2) : sizeof(float)) * G * 1024;
+  const size_t smem = sizeof(AgcShared<G>) + (LINEAR ? sizeof(float2) * 1024 : sizeof(float) * AGC_ROW) * G;
   static bool configured_dev[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -890,12 +1260,34 @@ static int launch_agc_g(const ChanLaunch& a, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 template <bool LINEAR>
-static int launch_agc(const ChanLaunch& a, cudaStream_t st) {
-  if (a.nwork <= 0) return 0;
+static int launch_agc_fused(const ChanLaunch& a, cudaStream_t st) {
   // one channel per CTA until the GPU (148 SMs x ~3 CTAs) is full, then pack to amortise the serial phases
   if (a.nwork >= 148 * 3 * 2) return launch_agc_g<LINEAR, 4>(a, st);
   if (a.nwork >= 148 * 3) return launch_agc_g<LINEAR, 2>(a, st);
   return launch_agc_g<LINEAR, 1>(a, st);
+}
+template <bool LINEAR>
+static int launch_agc(const ChanLaunch& a, cudaStream_t st) {
+  if (a.nwork <= 0) return 0;
+  const char* env = getenv("KA9Q_B200_AGC_FUSED");  // read per launch so a test can compare the two forms in one process
+  const bool fused = env && atoi(env) != 0;
+  if (fused || !a.agc_x) return launch_agc_fused<LINEAR>(a, st);
+  if (a.olen == 960)
+    agc_front_kernel<LINEAR, 960><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
+  else
+    agc_front_kernel<LINEAR, 0><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
+  {
+    static bool configured_dev[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured_dev[dev & 63]) {
+      cudaFuncSetAttribute(agc_serial_kernel<LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SerialShared));
+      configured_dev[dev & 63] = true;
+    }
+  }
+  agc_serial_kernel<LINEAR><<<(a.nwork + 31) / 32, SER_THREADS, sizeof(SerialShared), st>>>(a);
+  if (LINEAR) agc_output_kernel<LINEAR><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);  // AM: the serial kernel wrote the PCM
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 int launch_am(const ChanLaunch& a, cudaStream_t st) { return launch_agc<false>(a, st); }
 int launch_linear(const ChanLaunch& a, cudaStream_t st) { return launch_agc<true>(a, st); }

@@ -63,6 +63,11 @@ struct ka9q_stream {
   float2* d_resp = nullptr;
   float2* d_audio_resp = nullptr;
   float* d_audio_hist = nullptr;
+  // AM / linear scratch between the front, recurrence and output kernels: [max_blocks][n][olen]
+  float* d_agc_x_am = nullptr;
+  float* d_agc_x_lin = nullptr;
+  float2* d_agc_y_lin = nullptr;
+  float* d_agc_pow = nullptr;  // [max_blocks][n_am + n_lin][2]
   int16_t* d_pcm = nullptr;
   ChanStatus* d_status = nullptr;
   float2* d_filt = nullptr;
@@ -440,6 +445,15 @@ int ka9q_stream_commit(ka9q_stream* s) {
   if (upload_work(w_fm, &s->d_work_fm) || upload_work(w_am, &s->d_work_am) || upload_work(w_lin, &s->d_work_lin)) return -1;
   K9_CUDA(cudaMemcpy(s->d_params, s->h_params.data(), sizeof(ChanParams) * K, cudaMemcpyHostToDevice));
   K9_CUDA(cudaMemcpy(s->d_state, st.data(), sizeof(ChanState) * K, cudaMemcpyHostToDevice));
+  {
+    const size_t rows_am = (size_t)B * s->n_am, rows_lin = (size_t)B * s->n_lin;
+    if (rows_am) K9_CUDA(cudaMalloc(&s->d_agc_x_am, sizeof(float) * rows_am * s->olen));
+    if (rows_lin) {
+      K9_CUDA(cudaMalloc(&s->d_agc_x_lin, sizeof(float) * rows_lin * s->olen));
+      K9_CUDA(cudaMalloc(&s->d_agc_y_lin, sizeof(float2) * rows_lin * s->olen));
+    }
+    if (rows_am + rows_lin) K9_CUDA(cudaMalloc(&s->d_agc_pow, sizeof(float) * 2 * (rows_am + rows_lin)));
+  }
   if (any_fm) {
     // one ring per channel + a spare all-zero ring that stands in for the missing partner of an unpaired FM channel
     K9_CUDA(cudaMalloc(&s->d_audio_hist, sizeof(float) * (size_t)(K + 1) * NDEC));
@@ -623,6 +637,9 @@ static int issue_channels(ka9q_stream* s, int nblocks) {
     K9_CUDA(cudaStreamWaitEvent(s->s_am, s->e_fork, 0));
     a.work = s->d_work_am;
     a.nwork = s->n_am;
+    a.agc_x = s->d_agc_x_am;
+    a.agc_y = nullptr;
+    a.agc_pow = s->d_agc_pow;
     {
       TimedRegion tr(s, TC_AM, s->s_am);
       K9_CHECK(launch_am(a, s->s_am) == 0, "am kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -633,6 +650,9 @@ static int issue_channels(ka9q_stream* s, int nblocks) {
     K9_CUDA(cudaStreamWaitEvent(s->s_lin, s->e_fork, 0));
     a.work = s->d_work_lin;
     a.nwork = s->n_lin;
+    a.agc_x = s->d_agc_x_lin;
+    a.agc_y = s->d_agc_y_lin;
+    a.agc_pow = s->d_agc_pow + 2 * (size_t)s->cfg.max_blocks * s->n_am;
     {
       TimedRegion tr(s, TC_LIN, s->s_lin);
       K9_CHECK(launch_linear(a, s->s_lin) == 0, "linear kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -805,7 +825,7 @@ int ka9q_stream_destroy(ka9q_stream* s) {
   cudaDeviceSynchronize();
   bigfft_plan_destroy(&s->fwd);
   bigfft_plan_destroy(&s->p2048);
-  void* dev[] = {s->d_ring, s->d_spec, s->d_tmp0, s->d_tmp1, s->d_energy, s->d_tw2048, s->d_params, s->d_state, s->d_resp,
+  void* dev[] = {s->d_agc_x_am, s->d_agc_x_lin, s->d_agc_y_lin, s->d_agc_pow, s->d_ring, s->d_spec, s->d_tmp0, s->d_tmp1, s->d_energy, s->d_tw2048, s->d_params, s->d_state, s->d_resp,
                  s->d_audio_resp, s->d_audio_hist, s->d_pcm, s->d_status, s->d_filt, s->d_windows, s->d_work_fm,
                  s->d_work_am, s->d_work_lin};
   for (void* p : dev)

@@ -200,6 +200,34 @@ def test_other_overlap_geometries_against_reference(ref, L, M):
             assert rel_rms(filt[i], r.filt[:nb]) < FILT_TOL
 
 
+def test_split_and_fused_agc_kernels_are_bit_identical(monkeypatch):
+    """AM / linear run as front + per-lane recurrence + output kernels by default; the fused single-kernel form
+    (KA9Q_B200_AGC_FUSED=1) must give the same PCM and status bit for bit, also across batch boundaries, with more
+    than 32 channels per class (several recurrence warps, a partial last warp) and an olen that is not a multiple of 32."""
+    for L, M, nb in ((3840, 4353, 11), (4000, 4193, 7)):      # olen 960 and 1000
+        fs, D, N = 192000, 4, 8192
+        rng = np.random.default_rng(L)
+        n = nb * L
+        x = synth.awgn(rng, n, 0.02)
+        chans = []
+        for i in range(37):
+            k = -3000 + 160 * i
+            x = x + synth.am_carrier(n, fs, k * fs / N, 400.0 + 20 * i, 0.5, 0.01 + 0.001 * i)
+            chans.append((["AM", "USB", "IQ", "CWU", "ISB"][i % 5], k, {}))
+        t = np.arange(n) / fs
+        x = x * (1.0 + 0.8 * np.sin(2 * np.pi * 2.0 * t))       # slow fading: attack, hang and recovery all happen
+        cfg = dict(samprate=fs, D=D, L=L, M=M, N=N, iq=synth._quantize(x))
+        res = {}
+        for fused in ("0", "1"):
+            monkeypatch.setenv("KA9Q_B200_AGC_FUSED", fused)
+            c, pcm, st, _ = run_gpu(cfg, chans, nb, max_blocks=4, capture=False)
+            res[fused] = (pcm.copy(), st.copy())
+        assert np.array_equal(res["0"][0], res["1"][0])
+        for f in ("bb_power", "agc_gain", "reserved"):
+            assert np.array_equal(res["0"][1][f], res["1"][1][f], equal_nan=True), f
+        assert np.abs(res["0"][0]).max() > 1000
+
+
 def test_fm_squelch_closes_on_noise_like_the_reference(ref):
     cfg = synth.cfg1_fm(12)
     rng = np.random.default_rng(9)
