@@ -930,20 +930,24 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 8) agc_front_kernel(const Cha
   }
 }
 
-// One LANE per channel, 32 channels per CTA, and the per-sample work software-pipelined over five warps so that no
+// One LANE per channel, 32 channels per CTA, and the per-sample work software-pipelined over eight warps so that no
 // warp carries more than one short dependent chain or ~400 instructions per tile (a single warp doing everything needs
 // ~41 instructions and 131 cycles per sample: measured 0.27 ms per 4 blocks however few channels there are). Tiles of
-// 32 samples x 32 channels move through five stages, one barrier per step, four buffers deep:
-//   warp 0 (load)   tile s  : 32 coalesced 128-byte rows (prefetched one step ahead into registers) -> shared, transposed
+// 32 samples x 32 channels move through five stages (eight warps), one barrier per step, four buffers deep:
+//   warp 0 (load)   tile s  : 32 coalesced 128-byte rows -> shared, transposed, by cp.async issued three steps ahead (the
+//                             rows come from DRAM: one step is shorter than that latency)
 //   warp 1 (dc)     tile s-1: AM carrier-DC tracker (am.c:60): FADD + FFMA chain                       [AM only]
-//   warp 2 (div)    tile s-2: attack values headroom / x (IEEE division), which do not depend on the AGC state
-//   warp 3 (agc)    tile s-3: the gain / hang recurrence (am.c:62-73, linear.c:269-279), compare + select only
-//   warp 4 (store)  tile s-4: AM: (s - DC) * gain -> scaleclip -> int16 PCM rows; linear: gain rows back to the scratch
+//   warps 2-5 (div) tile s-2: attack values headroom / x, which do not depend on the AGC state. IEEE division compiles to
+//                             a ~70-cycle sequence with a guarded slow path that does not interleave with its
+//                             neighbours: 32 per lane in one warp made this the slowest stage (2800 cycles per step),
+//                             so four warps take 8 samples of the tile each
+//   warp 6 (agc)    tile s-3: the gain / hang recurrence (am.c:62-73, linear.c:269-279), compare + select only
+//   warp 7 (store)  tile s-4: AM: (s - DC) * gain -> scaleclip -> int16 PCM rows; linear: gain rows back to the scratch
 // grid = ceil(nwork / 32).
 constexpr int SER_TP = 33;       // padded tile row (floats)
-constexpr int SER_THREADS = 160;
+constexpr int SER_THREADS = 256;  // warps: 0 load, 1 dc, 2-5 div (8 samples of the tile each), 6 agc, 7 store
 struct SerialShared {
-  float x[4][32 * SER_TP];  // amplitude tiles [channel][sample]
+  float x[8][32 * SER_TP];  // amplitude tiles [channel][sample], filled by cp.async three steps ahead
   float q[4][32 * SER_TP];  // headroom / x, overwritten by the result (linear: gain; AM: (s - DC) * gain)
   float d[4][32 * SER_TP];  // AM: carrier level DC[n] (what the AGC follows)
   float o[4][32 * SER_TP];  // AM: s - DC
@@ -954,7 +958,10 @@ template <bool LINEAR>
 __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunch a) {
   extern __shared__ __align__(16) unsigned char ser_raw[];
   SerialShared& sh = *reinterpret_cast<SerialShared*>(ser_raw);
-  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // pipeline stage of this warp: 0 load, 1 dc, 2 div (warps 2..5, quarter `sub` of the tile each), 3 agc, 4 store
+  const int role = warp < 2 ? warp : (warp < 6 ? 2 : warp - 3);
+  const int sub = warp - 2;
   const int w0 = blockIdx.x * 32;
   const int nrows = min(32, a.nwork - w0);
   const int w = w0 + lane;
@@ -978,46 +985,58 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
   } else if (role == 0) {
     sh.pcm_off[lane] = 0;
   }
-  float nx[32];
-  // rows of tile T in the scratch: this lane's column of row r is tile_ptr(T) + r*olen
-  auto tile_ptr = [&](int T, int* cnt) -> float* {
-    const int b = T / tpb, k = T - b * tpb;
-    *cnt = min(32, olen - 32 * k);
+  // rows of tile (block b, tile k) in the scratch: this lane's column of row r is tile_ptr(b, k) + r*olen
+  auto tile_ptr = [&](int b, int k) -> float* {
     return a.agc_x + ((long long)b * a.nwork + w0) * olen + 32 * k + lane;
   };
-  auto fetch_tile = [&](int T) {
-    int cnt;
-    const float* g = tile_ptr(T, &cnt);
-    if (nrows == 32 && cnt == 32) {  // the usual case: no edge tests
+  // asynchronous transposed copy of a full tile (partial tiles are filled synchronously in their own step); always one
+  // commit group per call so the group count stays uniform. (ib, ik) walk the tiles in order: no division per step.
+  int ib = 0, ik = 0, iT = 0;
+  auto issue_next_tile = [&]() {
+    if (iT < ntiles) {
+      const int cnt = min(32, olen - 32 * ik);
+      if (nrows == 32 && cnt == 32) {
+        const float* g = tile_ptr(ib, ik);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sh.x[iT & 7] + lane);
 #pragma unroll
-      for (int r = 0; r < 32; r++) {
-        nx[r] = *g;
-        g += olen;
+        for (int r = 0; r < 32; r++) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst + 4u * (unsigned)(r * SER_TP)), "l"(g) : "memory");
+          g += olen;
+        }
       }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 32; r++) nx[r] = (r < nrows && lane < cnt) ? g[(long long)r * olen] : 1.f;
+      iT++;
+      if (++ik == tpb) {
+        ik = 0;
+        ib++;
+      }
     }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
-  if (role == 0 && ntiles > 0) fetch_tile(0);
+  if (role == 0) {
+    issue_next_tile();
+    issue_next_tile();
+    issue_next_tile();
+  }
   __syncthreads();
+  int b = 0, k = 0;  // block and tile-in-block of the tile this warp works on (advanced after every live step)
 #pragma unroll 1
   for (int s = 0; s < ntiles + 4; s++) {
     const int T = s - role;  // the tile this warp works on in this step
     const bool live = T >= 0 && T < ntiles;
-    const int k = live ? T % tpb : 0;
     const int cnt = min(32, olen - 32 * k);
     const int bi = T & 3;
     if (role == 0) {
-      if (live) {
-        float* xt = sh.x[bi];
-#pragma unroll
-        for (int r = 0; r < 32; r++) xt[r * SER_TP + lane] = nx[r];
-        if (T + 1 < ntiles) fetch_tile(T + 1);  // next tile's rows in flight during this step
+      issue_next_tile();
+      asm volatile("cp.async.wait_group 3;\n" ::: "memory");  // tile T has landed
+      if (live && !(nrows == 32 && cnt == 32)) {  // edge tile: plain loads, the unused slots get a harmless 1.0
+        const float* g = tile_ptr(b, k);
+        float* xt = sh.x[T & 7];
+#pragma unroll 4
+        for (int r = 0; r < 32; r++) xt[r * SER_TP + lane] = (r < nrows && lane < cnt) ? g[(long long)r * olen] : 1.f;
       }
     } else if (role == 1) {
       if (live && !LINEAR) {
-        const float* xt = sh.x[bi] + lane * SER_TP;
+        const float* xt = sh.x[T & 7] + lane * SER_TP;
         float* dt = sh.d[bi] + lane * SER_TP;
         float* ot = sh.o[bi] + lane * SER_TP;
         int i0 = 0;
@@ -1048,26 +1067,25 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
       }
     } else if (role == 2) {
       if (live) {
-        const float* xt = (LINEAR ? sh.x[bi] : sh.d[bi]) + lane * SER_TP;
-        float* qt = sh.q[bi] + lane * SER_TP;
-        int i0 = 0;
-#pragma unroll 1
-        for (; i0 + 8 <= cnt; i0 += 8) {
+        const float* xt = (LINEAR ? sh.x[T & 7] : sh.d[bi]) + lane * SER_TP + 8 * sub;
+        float* qt = sh.q[bi] + lane * SER_TP + 8 * sub;
+        const int m = min(8, cnt - 8 * sub);  // samples of this quarter inside the tile
+        if (m == 8) {
           float x[8];
 #pragma unroll
-          for (int i = 0; i < 8; i++) x[i] = xt[i0 + i];
+          for (int i = 0; i < 8; i++) x[i] = xt[i];
 #pragma unroll
           for (int i = 0; i < 8; i++) x[i] = headroom / x[i];
 #pragma unroll
-          for (int i = 0; i < 8; i++) qt[i0 + i] = x[i];
-        }
+          for (int i = 0; i < 8; i++) qt[i] = x[i];
+        } else {
 #pragma unroll 1
-        for (; i0 < cnt; i0++) qt[i0] = headroom / xt[i0];
+          for (int i = 0; i < m; i++) qt[i] = headroom / xt[i];
+        }
       }
     } else if (role == 3) {
       if (live) {
-        const int b = T / tpb;
-        const float* xt = (LINEAR ? sh.x[bi] : sh.d[bi]) + lane * SER_TP;
+        const float* xt = (LINEAR ? sh.x[T & 7] : sh.d[bi]) + lane * SER_TP;
         const float* ot = sh.o[bi] + lane * SER_TP;
         float* qt = sh.q[bi] + lane * SER_TP;
         // am.c:62-73 / linear.c:269-279, same operands and order as the reference, written with selects. The start-up
@@ -1128,11 +1146,9 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
       }
     } else {
       if (live) {
-        const int b = T / tpb;
         const float* qt = sh.q[bi] + lane;
         if (LINEAR) {
-          int dummy;
-          float* g = tile_ptr(T, &dummy);
+          float* g = tile_ptr(b, k);
 #pragma unroll 8
           for (int r = 0; r < nrows; r++)
             if (lane < cnt) g[(long long)r * olen] = qt[r * SER_TP];
@@ -1144,6 +1160,10 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
             if (lane < cnt) pcm_blk[sh.pcm_off[r]] = scaleclip(qt[r * SER_TP]);
         }
       }
+    }
+    if (live && ++k == tpb) {
+      k = 0;
+      b++;
     }
     __syncthreads();
   }
@@ -1271,7 +1291,9 @@ static int launch_agc(const ChanLaunch& a, cudaStream_t st) {
   if (a.nwork <= 0) return 0;
   const char* env = getenv("KA9Q_B200_AGC_FUSED");  // read per launch so a test can compare the two forms in one process
   const bool fused = env && atoi(env) != 0;
-  if (fused || !a.agc_x) return launch_agc_fused<LINEAR>(a, st);
+  // the recurrence kernel takes ~0.15 ms per 4 blocks however few channels there are (its pipeline is latency-bound);
+  // below ~1000 channels the fused kernel with one channel per CTA is as fast or faster
+  if (fused || !a.agc_x || (a.nwork < 1024 && !(env && atoi(env) == 0))) return launch_agc_fused<LINEAR>(a, st);
   if (a.olen == 960)
     agc_front_kernel<LINEAR, 960><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
   else
