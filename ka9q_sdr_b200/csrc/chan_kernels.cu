@@ -21,9 +21,6 @@ namespace k9 {
 
 // ---------------------------------------------------------------- common device helpers
 
-#ifndef K9_AGC_BLOCK_PIPELINE_DEFAULT
-#define K9_AGC_BLOCK_PIPELINE_DEFAULT 0  // flipped to 1 once measured
-#endif
 #ifndef FM_FEWER_BARRIERS
 #define FM_FEWER_BARRIERS 1
 #endif
@@ -1297,60 +1294,24 @@ static int launch_agc(const ChanLaunch& a, cudaStream_t st) {
   // the recurrence kernel takes ~0.15 ms per 4 blocks however few channels there are (its pipeline is latency-bound);
   // below ~1000 channels the fused kernel with one channel per CTA is as fast or faster
   if (fused || !a.agc_x || (a.nwork < 1024 && !(env && atoi(env) == 0))) return launch_agc_fused<LINEAR>(a, st);
-  // Block by block on two streams: the front kernel of block b+1 (throughput-bound, fills the GPU) runs beside the
-  // recurrence (+ output) kernels of block b (latency-bound, 8 warps per 32 channels). The per-channel state crosses
-  // the launches through the state array, exactly as it crosses batches.
-  struct Aux {
-    cudaStream_t s = nullptr;
-    cudaEvent_t start = nullptr, end = nullptr, front[64] = {};
-  };
-  static Aux aux_dev[64];
-  int dev = 0;
-  cudaGetDevice(&dev);
-  Aux& x = aux_dev[dev & 63];
-  if (!x.s) {
-    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return -1;
-    cudaEventCreateWithFlags(&x.start, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&x.end, cudaEventDisableTiming);
-    for (auto& e : x.front) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    cudaFuncSetAttribute(agc_serial_kernel<LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SerialShared));
+  // (Tried: block by block on two streams, the front kernel of block b+1 beside the recurrence of block b. Measured
+  // slower, 0.374 vs 0.351 ms at 8192 AM channels: the front kernel fills every SM, so the recurrence CTAs only get in
+  // once it drains, and the per-block launches add their own fill / drain.)
+  {
+    static bool configured_dev[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured_dev[dev & 63]) {
+      cudaFuncSetAttribute(agc_serial_kernel<LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SerialShared));
+      configured_dev[dev & 63] = true;
+    }
   }
-  if (a.nblocks > 64) return launch_agc_fused<LINEAR>(a, st);
-  const char* envp = getenv("KA9Q_B200_AGC_BLOCK_PIPELINE");
-  if (!(envp ? atoi(envp) != 0 : K9_AGC_BLOCK_PIPELINE_DEFAULT)) {  // one stream, all blocks per kernel
-    if (a.olen == 960)
-      agc_front_kernel<LINEAR, 960><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
-    else
-      agc_front_kernel<LINEAR, 0><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
-    agc_serial_kernel<LINEAR><<<(a.nwork + 31) / 32, SER_THREADS, sizeof(SerialShared), st>>>(a);
-    if (LINEAR) agc_output_kernel<LINEAR><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-  }
-  cudaEventRecord(x.start, st);
-  cudaStreamWaitEvent(x.s, x.start, 0);
-  for (int b = 0; b < a.nblocks; b++) {
-    ChanLaunch ab = a;  // block b as a one-block launch
-    ab.nblocks = 1;
-    ab.block0 = a.block0 + b;
-    ab.start0 = (int)(((long long)a.start0 + (long long)b * (a.L % a.N)) % a.N);
-    ab.spec = a.spec + (long long)b * a.spec_stride;
-    ab.pcm = a.pcm + (long long)b * a.pcm_stride;
-    ab.status = a.status + (long long)b * a.nchan_total;
-    if (a.filt_dbg) ab.filt_dbg = a.filt_dbg + (long long)b * a.nchan_total * a.olen;
-    ab.agc_x = a.agc_x + (long long)b * a.nwork * a.olen;
-    if (a.agc_y) ab.agc_y = a.agc_y + (long long)b * a.nwork * a.olen;
-    ab.agc_pow = a.agc_pow + 2ll * b * a.nwork;
-    if (a.olen == 960)
-      agc_front_kernel<LINEAR, 960><<<a.nwork, FFT2048_THREADS, 0, st>>>(ab);
-    else
-      agc_front_kernel<LINEAR, 0><<<a.nwork, FFT2048_THREADS, 0, st>>>(ab);
-    cudaEventRecord(x.front[b], st);
-    cudaStreamWaitEvent(x.s, x.front[b], 0);
-    agc_serial_kernel<LINEAR><<<(a.nwork + 31) / 32, SER_THREADS, sizeof(SerialShared), x.s>>>(ab);
-    if (LINEAR) agc_output_kernel<LINEAR><<<a.nwork, FFT2048_THREADS, 0, x.s>>>(ab);  // AM: the recurrence kernel wrote the PCM
-  }
-  cudaEventRecord(x.end, x.s);
-  cudaStreamWaitEvent(st, x.end, 0);
+  if (a.olen == 960)
+    agc_front_kernel<LINEAR, 960><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
+  else
+    agc_front_kernel<LINEAR, 0><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
+  agc_serial_kernel<LINEAR><<<(a.nwork + 31) / 32, SER_THREADS, sizeof(SerialShared), st>>>(a);
+  if (LINEAR) agc_output_kernel<LINEAR><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);  // AM: the recurrence kernel wrote the PCM
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 int launch_am(const ChanLaunch& a, cudaStream_t st) { return launch_agc<false>(a, st); }

@@ -8,7 +8,7 @@ from ka9q_sdr_b200 import channelizer as ch
 plan = bench.make_plan("cfg5", None)
 B = 4
 iq = bench.make_input(plan, B)
-for mode, K in (("AM", 8192), ("USB", 8192), ("AM", 1024)):
+for mode, K in (("FM", 8192), ("AM", 8192), ("USB", 8192), ("IQ", 8192), ("AM", 1024), ("USB", 1024)):
     c = ch.Channelizer(plan.samprate, plan.L, plan.M, plan.D, max_blocks=B)
     for s in plan.channels[:K]:
         c.add_channel(mode, s.bin, low=(s.low if mode == "FM" else None), high=(s.high if mode == "FM" else None))
