@@ -944,7 +944,8 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 8) agc_front_kernel(const Cha
 //   warp 6 (agc)    tile s-3: the gain / hang recurrence (am.c:62-73, linear.c:269-279), compare + select only
 //   warp 7 (store)  tile s-4: AM: (s - DC) * gain -> scaleclip -> int16 PCM rows; linear: gain rows back to the scratch
 // grid = ceil(nwork / 32).
-constexpr int SER_TP = 33;       // padded tile row (floats)
+constexpr int SER_TP = 36;       // tile row pitch (floats): 16-byte aligned rows, 128-bit row accesses of the 32 lanes
+                                 // (one row per lane, 144 bytes apart) are bank-conflict free per quarter-warp
 constexpr int SER_THREADS = 256;  // warps: 0 load, 1 dc, 2-5 div (8 samples of the tile each), 6 agc, 7 store
 struct SerialShared {
   float x[8][32 * SER_TP];  // amplitude tiles [channel][sample], filled by cp.async three steps ahead
@@ -953,6 +954,16 @@ struct SerialShared {
   float o[4][32 * SER_TP];  // AM: s - DC
   int pcm_off[32];
 };
+
+__device__ __forceinline__ void ld8(float (&x)[8], const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+  x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&x)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(x[4], x[5], x[6], x[7]);
+}
 
 template <bool LINEAR>
 __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunch a) {
@@ -1043,19 +1054,15 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
 #pragma unroll 1
         for (; i0 + 8 <= cnt; i0 += 8) {  // batches of 8: loads, chain, stores
           float x[8], dd[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) x[i] = xt[i0 + i];
+          ld8(x, xt + i0);
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             dc += 0.0001f * (x[i] - dc);  // am.c:60
             dd[i] = dc;                   // the AGC follows the carrier level (am.c:62)
             x[i] = x[i] - dc;             // s - DC (am.c:74)
           }
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            dt[i0 + i] = dd[i];
-            ot[i0 + i] = x[i];
-          }
+          st8(dt + i0, dd);
+          st8(ot + i0, x);
         }
 #pragma unroll 1
         for (; i0 < cnt; i0++) {  // olen not a multiple of 8
@@ -1072,12 +1079,10 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
         const int m = min(8, cnt - 8 * sub);  // samples of this quarter inside the tile
         if (m == 8) {
           float x[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) x[i] = xt[i];
+          ld8(x, xt);
 #pragma unroll
           for (int i = 0; i < 8; i++) x[i] = headroom / x[i];
-#pragma unroll
-          for (int i = 0; i < 8; i++) qt[i] = x[i];
+          st8(qt, x);
         } else {
 #pragma unroll 1
           for (int i = 0; i < m; i++) qt[i] = headroom / xt[i];
@@ -1112,16 +1117,16 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
 #pragma unroll 1
           for (; i0 + 8 <= cnt; i0 += 8) {
             float x[8], q[8], o[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-              x[i] = xt[i0 + i];
-              q[i] = qt[i0 + i];
-              o[i] = LINEAR ? 0.f : ot[i0 + i];
-            }
+            ld8(x, xt + i0);
+            ld8(q, qt + i0);
+            if (!LINEAR) ld8(o, ot + i0);
 #pragma unroll
             for (int i = 0; i < 8; i++) q[i] = agc_step(x[i], q[i]);
+            if (!LINEAR) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) qt[i0 + i] = LINEAR ? q[i] : o[i] * q[i];
+              for (int i = 0; i < 8; i++) q[i] = o[i] * q[i];
+            }
+            st8(qt + i0, q);
           }
         }
 #pragma unroll 1
