@@ -1182,61 +1182,62 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
   }
 }
 
-// parallel output: gain / shift / quantise (linear.c:280-299, am.c:74, audio.c:22-28); one CTA per channel
+// parallel output: gain / shift / quantise (linear.c:280-299, am.c:74, audio.c:22-28); one CTA per channel and block
+// (a pure stream whose rate is set by the loads in flight: one CTA per channel looping over the blocks ran at 3.3 TB/s)
 template <bool LINEAR>
 __global__ void __launch_bounds__(FFT2048_THREADS) agc_output_kernel(const ChanLaunch a) {
   const int t = threadIdx.x;
-  const int w = blockIdx.x;
+  const int w = blockIdx.x, b = blockIdx.y;
   const int c = a.work[w].x;
   const int olen = a.olen;
   const ChanParams& P = a.params[c];
-  const int pcm_off = P.pcm_off;
-  const double shift_cycles = LINEAR ? P.shift_cycles : 0.0;
+  const long long row = (long long)b * a.nwork + w;
+  const float* __restrict__ g = a.agc_x + row * olen;
+  int16_t* __restrict__ pcm_row = a.pcm + (long long)b * a.pcm_stride + P.pcm_off;
+  if (!LINEAR) {
+    for (int o = t; o < olen; o += FFT2048_THREADS) pcm_row[o] = scaleclip(g[o]);  // am.c:74
+    return;
+  }
+  const double shift_cycles = P.shift_cycles;
   const bool shifted = shift_cycles != 0.0;
-  const double shift_phase = shifted ? a.state[c].shift_phase : 0.0;
   const int nch = P.channels;
-  int e = LINEAR ? phase_index0(P.bin, a.start0, a.N) : 0;
-  const int phase_step = P.phase_step;
-#pragma unroll 1
-  for (int b = 0; b < a.nblocks; b++) {
-    const long long row = (long long)b * a.nwork + w;
-    const float* g = a.agc_x + row * olen;
-    int16_t* pcm_row = a.pcm + (long long)b * a.pcm_stride + pcm_off;
-    if (!LINEAR) {
-      for (int o = t; o < olen; o += FFT2048_THREADS) pcm_row[o] = scaleclip(g[o]);  // am.c:74
+  int e = phase_index0(P.bin, a.start0, a.N);
+  for (int i = 0; i < b; i++) e = phase_advance(e, P.phase_step, a.N);
+  const float2 ph = phase_from_index(a, e);
+  // the shift oscillator's phase at the start of the launch; agc_shift_advance_kernel moves it on afterwards
+  const double phase0 = shifted ? a.state[c].shift_phase + shift_cycles * (double)olen * b : 0.0;
+  const float2* __restrict__ yk = a.agc_y + row * olen;
+  for (int o = t; o < olen; o += FFT2048_THREADS) {
+    const float gn = g[o];
+    const float2 y = cmul(yk[o], ph);            // the block's LO phase rides the gain multiply
+    float2 z = make_float2(y.x * gn, y.y * gn);  // linear.c:280
+    if (shifted) {
+      // post-detection shift oscillator (linear.c:283-289, osc.c:39-51): phasor(n) = exp(j*2*pi*f*n), n counted
+      // from the first sample the oscillator was stepped on
+      double p = phase0 + shift_cycles * (double)o;
+      p -= floor(p);
+      double sn, cs;
+      sincospi(2.0 * p, &sn, &cs);
+      z = cmul(z, make_float2((float)cs, (float)sn));
+    }
+    if (nch == 1) {
+      pcm_row[o] = scaleclip(z.x);  // linear.c:291-296
     } else {
-      const float2* yk = a.agc_y + row * olen;
-      const float2 ph = phase_from_index(a, e);
-      const double phase0 = shifted ? shift_phase + shift_cycles * (double)olen * b : 0.0;
-      for (int o = t; o < olen; o += FFT2048_THREADS) {
-        const float gn = g[o];
-        const float2 y = cmul(yk[o], ph);            // the block's LO phase rides the gain multiply
-        float2 z = make_float2(y.x * gn, y.y * gn);  // linear.c:280
-        if (shifted) {
-          // post-detection shift oscillator (linear.c:283-289, osc.c:39-51): phasor(n) = exp(j*2*pi*f*n), n counted
-          // from the first sample the oscillator was stepped on
-          double p = phase0 + shift_cycles * (double)o;
-          p -= floor(p);
-          double sn, cs;
-          sincospi(2.0 * p, &sn, &cs);
-          z = cmul(z, make_float2((float)cs, (float)sn));
-        }
-        if (nch == 1) {
-          pcm_row[o] = scaleclip(z.x);  // linear.c:291-296
-        } else {
-          pcm_row[2 * o] = scaleclip(z.x);  // I left, Q right (linear.c:299)
-          pcm_row[2 * o + 1] = scaleclip(z.y);
-        }
-      }
-      e = phase_advance(e, phase_step, a.N);
+      pcm_row[2 * o] = scaleclip(z.x);  // I left, Q right (linear.c:299)
+      pcm_row[2 * o + 1] = scaleclip(z.y);
     }
   }
-  if (LINEAR && shifted) {
-    __syncthreads();  // every thread has read the starting phase
-    if (t == 0) {
-      const double ph = shift_phase + shift_cycles * (double)olen * a.nblocks;
-      a.state[c].shift_phase = ph - floor(ph);
-    }
+}
+
+// after the output kernel: the shift oscillators have run olen * nblocks samples further
+__global__ void agc_shift_advance_kernel(const ChanLaunch a) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= a.nwork) return;
+  const int c = a.work[w].x;
+  const double shift_cycles = a.params[c].shift_cycles;
+  if (shift_cycles != 0.0) {
+    const double ph = a.state[c].shift_phase + shift_cycles * (double)a.olen * a.nblocks;
+    a.state[c].shift_phase = ph - floor(ph);
   }
 }
 
@@ -1316,7 +1317,10 @@ static int launch_agc(const ChanLaunch& a, cudaStream_t st) {
   else
     agc_front_kernel<LINEAR, 0><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
   agc_serial_kernel<LINEAR><<<(a.nwork + 31) / 32, SER_THREADS, sizeof(SerialShared), st>>>(a);
-  if (LINEAR) agc_output_kernel<LINEAR><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);  // AM: the recurrence kernel wrote the PCM
+  if (LINEAR) {  // AM: the recurrence kernel wrote the PCM
+    agc_output_kernel<LINEAR><<<dim3(a.nwork, a.nblocks), FFT2048_THREADS, 0, st>>>(a);
+    agc_shift_advance_kernel<<<(a.nwork + 127) / 128, 128, 0, st>>>(a);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 int launch_am(const ChanLaunch& a, cudaStream_t st) { return launch_agc<false>(a, st); }
