@@ -241,6 +241,10 @@ int ka9q_stream_sync(ka9q_stream *s);
 /* wait only for the D2H copies issued by ka9q_stream_fetch (PCM/status are double-buffered on the device, so the next
  * batch may already be computing): the steady-state loop is push(k+2); compute(k+1); fetch(k); wait_fetch() */
 int ka9q_stream_wait_fetch(ka9q_stream *s);
+/* wait for the fetch issued `batches_ago` fetches ago (0 = the latest, 1 = the one before): lets the host queue the
+ * copy-out of batch k behind that of batch k-1 and only then wait for k-1, so the D2H link never idles on a host round
+ * trip: push(k+1); compute(k); fetch(k); wait_fetched(1) -> batch k-1 is in host memory */
+int ka9q_stream_wait_fetched(ka9q_stream *s, int batches_ago);
 /* Time of the device work of the last compute call in milliseconds (CUDA events on the compute stream), and of
  * the dominant (channel) kernels alone. Valid after ka9q_stream_sync. */
 int ka9q_stream_last_timing(ka9q_stream *s, float *total_ms, float *fft_ms, float *chan_ms);

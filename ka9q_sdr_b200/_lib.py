@@ -63,7 +63,7 @@ EXPORTED = [
     "ka9q_fft_plan_describe", "ka9q_hb15_cascade", "ka9q_host_alloc", "ka9q_host_free", "ka9q_stream_timer_start",
     "ka9q_stream_timer_stop", "ka9q_osc_run", "ka9q_stream_wait_fetch", "ka9q_stream_compute_fft_blocks",
     "ka9q_stream_nccl_allgather_spectrum", "ka9q_stream_set_overlap", "ka9q_ingest_init", "ka9q_ingest_datagram",
-    "ka9q_rtp_process", "ka9q_pcm_packetise",
+    "ka9q_rtp_process", "ka9q_pcm_packetise", "ka9q_stream_wait_fetched",
 ]
 
 
@@ -103,6 +103,7 @@ def lib():
     L.ka9q_stream_compute_fft_blocks.argtypes = [vp, ci, ci, ci]
     L.ka9q_stream_nccl_allgather_spectrum.argtypes = [vp, ci]
     L.ka9q_stream_wait_fetch.argtypes = [vp]
+    L.ka9q_stream_wait_fetched.argtypes = [vp, ci]
     L.ka9q_stream_last_timing.argtypes = [vp, C.POINTER(cf), C.POINTER(cf), C.POINTER(cf)]
     L.ka9q_stream_spectrum_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(cll)]
     L.ka9q_nccl_unique_id.argtypes = [vp]

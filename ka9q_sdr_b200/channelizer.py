@@ -158,6 +158,10 @@ class Channelizer:
     def wait_fetch(self):
         _lib.check(self.lib.ka9q_stream_wait_fetch(self.h), "ka9q_stream_wait_fetch")
 
+    def wait_fetched(self, batches_ago: int = 0):
+        """Wait for the fetch issued `batches_ago` fetches ago (0 or 1)."""
+        _lib.check(self.lib.ka9q_stream_wait_fetched(self.h, batches_ago), "ka9q_stream_wait_fetched")
+
     def sync(self):
         _lib.check(self.lib.ka9q_stream_sync(self.h), "ka9q_stream_sync")
 

@@ -745,6 +745,15 @@ int ka9q_stream_wait_fetch(ka9q_stream* s) {
   return 0;
 }
 
+int ka9q_stream_wait_fetched(ka9q_stream* s, int batches_ago) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  K9_CHECK(batches_ago == 0 || batches_ago == 1, "batches_ago must be 0 or 1 (the device PCM is double-buffered)");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  // e_fetched[p] is recorded behind the copies of the batch computed into PCM buffer p; comp_parity is the latest batch's
+  K9_CUDA(cudaEventSynchronize(s->e_fetched[s->comp_parity ^ batches_ago]));
+  return 0;
+}
+
 int ka9q_stream_sync(ka9q_stream* s) {
   K9_CHECK(s && s->committed, "stream not committed");
   K9_CUDA(cudaSetDevice(s->cfg.device));
