@@ -220,9 +220,12 @@ def test_split_and_fused_agc_kernels_are_bit_identical(monkeypatch):
         res = {}
         for fused in ("0", "1"):
             monkeypatch.setenv("KA9Q_B200_AGC_FUSED", fused)
-            c, pcm, st, _ = run_gpu(cfg, chans, nb, max_blocks=4, capture=False)
-            res[fused] = (pcm.copy(), st.copy())
+            c, pcm, st, filt = run_gpu(cfg, chans, nb, max_blocks=4, capture=True)
+            res[fused] = (pcm.copy(), st.copy(), filt)
         assert np.array_equal(res["0"][0], res["1"][0])
+        for i, (mode, _, _) in enumerate(chans):   # the debug capture of the filter output takes a separate path in each form
+            if mode != "ISB":                      # (no capture for CROSS_CONJ outputs: two sidebands, not one signal)
+                assert np.array_equal(res["0"][2][i], res["1"][2][i]), i
         for f in ("bb_power", "agc_gain", "reserved"):
             assert np.array_equal(res["0"][1][f], res["1"][1][f], equal_nan=True), f
         assert np.abs(res["0"][0]).max() > 1000
