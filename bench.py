@@ -145,6 +145,41 @@ def bind_to_gpu_numa_node(gpu_index: int):
     return None
 
 
+def run_cpu_channelizer(plan, iq_blocks: np.ndarray, nsample: int = 1024):
+    """Second CPU figure, clearly NOT the reference: the shared-FFT channelizer restated in numpy/scipy
+    (oracle/channelizer_port.py: one forward FFT per block, rotated windows, vectorised over channels) on the host cores,
+    so that the algorithmic gain (shared FFT) and the hardware gain (B200 vs CPU) can be told apart. Bounded sample: the
+    forward FFT of every block is done in full, the channel part on `nsample` of the plan's channels and scaled."""
+    from oracle import channelizer_port as cp
+    fm = [c for c in plan.channels if c.mode in ("FM", "NBFM")]
+    if len(fm) != len(plan.channels) or not fm:
+        return None
+    cores = os.cpu_count() or 1
+    sub = fm[:: max(1, len(fm) // nsample)][:nsample]
+    ch = cp.FmChannelizer(plan.samprate, plan.L, plan.M, plan.D, [c.bin for c in sub], sub[0].low, sub[0].high, workers=cores)
+    nb = iq_blocks.size // (2 * plan.L)
+    import scipy.fft as sfft
+    t_fft = t_all = 0.0
+    for b in range(nb):
+        blk = iq_blocks[2 * b * plan.L:2 * (b + 1) * plan.L]
+        t0 = time.perf_counter()
+        ch.process(blk)
+        dt = time.perf_counter() - t0
+        if b:                           # block 0 warms the FFT plans up
+            t_all += dt
+            x = np.zeros(plan.N, dtype=np.complex64)
+            t0 = time.perf_counter()
+            sfft.fft(x, workers=cores)
+            t_fft += time.perf_counter() - t0
+    nt = nb - 1
+    per_block = t_fft / nt + (t_all - t_fft) / nt * (len(fm) / len(sub))       # full plan: one FFT + all channels
+    value = len(fm) * (plan.L / 1e6) / per_block
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "what": "shared-FFT channelizer restated in numpy/scipy (oracle/channelizer_port.py) - NOT the reference",
+            "sample": f"{nt} blocks: full forward FFT + {len(sub)} of {len(fm)} channels, channel part scaled linearly",
+            "fft_ms_per_block": 1e3 * t_fft / nt, "channels_ms_per_block_full_plan": 1e3 * (t_all - t_fft) / nt * len(fm) / len(sub)}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 
 def run_reference(args, plan, emit=True):
@@ -422,6 +457,12 @@ def run_ours(args, plan):
             cpu = run_reference(ra, plan, emit=False).get("cpu_baseline")
         except Exception as e:  # the GPU numbers stand on their own
             cpu = {"error": str(e)}
+    cpu_chan = None
+    if not multi and not args.no_cpu_baseline:
+        try:
+            cpu_chan = run_cpu_channelizer(plan, np.asarray(pin_in.array[:2 * min(B, 3) * plan.L]))
+        except Exception as e:
+            cpu_chan = {"error": str(e)}
 
     launches_per_step = c.launches_per_call + (1 if multi else 0)
     work_mb = (K * 2048 * 8 + K * 2048 * 4 + B * plan.N * 8 * 2 + B * c.pcm_stride * 2) / 1e6
@@ -444,6 +485,7 @@ def run_ours(args, plan):
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "cpu_channelizer": cpu_chan,
         "realtime_channels": ms_blocks_per_s / (plan.samprate / 1e6),
         "speedup_over_realtime": (B * 20.0) / ms_per_step,
         "class_ms_per_step": {k: v[0] / nser for k, v in classes.items()},

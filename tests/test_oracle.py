@@ -194,3 +194,26 @@ def test_reference_zero_fills_lost_packets_and_keeps_lo_phase(ref):
     iq2[2 * 5 * pkt:2 * 6 * pkt] = 0
     b = ref.chain_run("FM", fs, L, M, D, iq2, carrier_hz=k * fs / N, lo_cycles=-k / N, pkt_samples=pkt)
     assert np.array_equal(a.pcm, b.pcm)
+
+
+def test_cpu_channelizer_restatement_matches_the_per_channel_port():
+    """oracle/channelizer_port.py (shared forward FFT + bin rotation, vectorised over channels: the algorithm the GPU path
+    runs, used by bench.py as the second CPU figure) against oracle/port.py (the reference's mix-then-FFT order, one
+    channel at a time) on three FM channels of one stream: same PCM within 1 LSB."""
+    from oracle import channelizer_port as cp
+    from ka9q_sdr_b200 import synth
+    fs, D, L, M, N, nb = 192000, 4, 3840, 4353, 8192, 6
+    rng = np.random.default_rng(11)
+    n = nb * L
+    bins = [2048, -1536, 300]
+    x = synth.awgn(rng, n, 0.01)
+    for i, k in enumerate(bins):
+        x = x + synth.fm_carrier(n, fs, k * fs / N, 700.0 + 200 * i, 2500.0, 0.2)
+    iq = synth._quantize(x)
+    ch = cp.FmChannelizer(fs, L, M, D, bins, -8000.0, 8000.0, workers=1)
+    got = np.concatenate([ch.process(iq[2 * b * L:2 * (b + 1) * L]) for b in range(nb)], axis=1)
+    for i, k in enumerate(bins):
+        want = port.run_channel("FM", fs, L, M, D, iq, k)["pcm"]
+        d = np.abs(got[i].astype(np.int32) - want.astype(np.int32))
+        assert d.max() <= 1, (k, d.max())
+        assert np.abs(want).max() > 1000
