@@ -342,6 +342,14 @@ typedef int (*ka9q_emit_fn)(void *user, const void *packet, int len); /* return 
  * arguments. */
 int ka9q_pcm_packetise(ka9q_pcm_out *out, const int16_t *pcm, int frames, int channels, ka9q_emit_fn emit, void *user);
 
+/* Status side: the "signals" and demodulator section of the TLV status list that `radio` multicasts
+ * (radio_status.c:171-203, encodings status.c:31-96: type byte, length byte, big-endian value with leading zero bytes
+ * suppressed, EOL = 0 terminates), from one ka9q_chan_status row. Fields this library does not compute (NOISE_DENSITY,
+ * PL_TONE, the PLL group) are left out; the delta compression of radio_status.c:compact_packet is the sender's business.
+ * demod_type: 0 linear, 1 AM, 2 FM (radio.h:26-30). Returns the number of bytes written, -1 if `room` is too small. */
+int ka9q_status_encode_signals(const ka9q_chan_status *st, int demod_type, int isb, float if_power, float noise_bandwidth,
+                               int output_channels, unsigned char *buf, int room);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,7 +63,7 @@ EXPORTED = [
     "ka9q_fft_plan_describe", "ka9q_hb15_cascade", "ka9q_host_alloc", "ka9q_host_free", "ka9q_stream_timer_start",
     "ka9q_stream_timer_stop", "ka9q_osc_run", "ka9q_stream_wait_fetch", "ka9q_stream_compute_fft_blocks",
     "ka9q_stream_nccl_allgather_spectrum", "ka9q_stream_set_overlap", "ka9q_ingest_init", "ka9q_ingest_datagram",
-    "ka9q_rtp_process", "ka9q_pcm_packetise", "ka9q_stream_wait_fetched",
+    "ka9q_rtp_process", "ka9q_pcm_packetise", "ka9q_stream_wait_fetched", "ka9q_status_encode_signals",
 ]
 
 

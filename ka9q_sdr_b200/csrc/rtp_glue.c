@@ -159,3 +159,68 @@ int ka9q_pcm_packetise(ka9q_pcm_out *o, const int16_t *pcm, int frames, int chan
   }
   return sent;
 }
+
+// ---- status TLV (status.c:31-96, radio_status.c:171-203; enum status_type status.h:6-70) ----
+enum {
+  // positions in enum status_type (status.h:6-70); tests/test_rtp_glue.py re-derives them from the reference header
+  ST_EOL = 0, ST_NOISE_BANDWIDTH = 35, ST_IF_POWER = 36, ST_BASEBAND_POWER = 37, ST_DEMOD_MODE = 40,
+  ST_INDEPENDENT_SIDEBAND = 41, ST_DEMOD_SNR = 42, ST_DEMOD_GAIN = 43, ST_FREQ_OFFSET = 44, ST_PEAK_DEVIATION = 45,
+  ST_OUTPUT_CHANNELS = 50
+};
+
+// encode_int64 (status.c:31-51): type, length, value big-endian with the leading zero bytes dropped
+static unsigned char *tlv_int(unsigned char *cp, int type, uint64_t x) {
+  *cp++ = (unsigned char)type;
+  int len = 8;
+  while (len > 0 && (x & 0xff00000000000000ULL) == 0) {
+    x <<= 8;
+    len--;
+  }
+  *cp++ = (unsigned char)len;
+  for (int i = 0; i < len; i++) {
+    *cp++ = (unsigned char)(x >> 56);
+    x <<= 8;
+  }
+  return cp;
+}
+static unsigned char *tlv_float(unsigned char *cp, int type, float x) {  // encode_float (status.c:83-88)
+  uint32_t d;
+  memcpy(&d, &x, sizeof d);
+  return tlv_int(cp, type, d);
+}
+static unsigned char *tlv_byte(unsigned char *cp, int type, unsigned char x) {  // encode_byte (status.c:62-69)
+  *cp++ = (unsigned char)type;
+  *cp++ = 1;
+  *cp++ = x;
+  return cp;
+}
+
+int ka9q_status_encode_signals(const ka9q_chan_status *st, int demod_type, int isb, float if_power, float noise_bandwidth,
+                               int output_channels, unsigned char *buf, int room) {
+  if (!st || !buf) return -1;
+  unsigned char tmp[96], *cp = tmp;  // at most 10 items of <= 6 bytes and the EOL
+  cp = tlv_float(cp, ST_NOISE_BANDWIDTH, noise_bandwidth);    // radio_status.c:171
+  cp = tlv_float(cp, ST_IF_POWER, if_power);                  // :174
+  cp = tlv_float(cp, ST_BASEBAND_POWER, st->bb_power);        // :175
+  cp = tlv_byte(cp, ST_DEMOD_MODE, (unsigned char)demod_type);  // :181
+  switch (demod_type) {
+    case 1:  // AM_DEMOD (:183-185)
+      cp = tlv_float(cp, ST_DEMOD_GAIN, st->agc_gain);
+      break;
+    case 2:  // FM_DEMOD (:186-191; PL_TONE is not computed here)
+      cp = tlv_float(cp, ST_PEAK_DEVIATION, st->pdeviation);
+      cp = tlv_float(cp, ST_FREQ_OFFSET, st->foffset);
+      cp = tlv_float(cp, ST_DEMOD_SNR, st->snr);
+      break;
+    default:  // LINEAR_DEMOD (:192-202, no PLL)
+      cp = tlv_float(cp, ST_DEMOD_GAIN, st->agc_gain);
+      cp = tlv_int(cp, ST_INDEPENDENT_SIDEBAND, (uint32_t)isb);
+      break;
+  }
+  cp = tlv_int(cp, ST_OUTPUT_CHANNELS, (uint32_t)output_channels);  // :204
+  *cp++ = ST_EOL;                                                   // :205
+  const int n = (int)(cp - tmp);
+  if (n > room) return -1;
+  memcpy(buf, tmp, (size_t)n);
+  return n;
+}

@@ -562,3 +562,32 @@ int ref_glue_send(int channels, long long *state5, const float *buf, int frames,
   free(demod);
   return n;
 }
+
+/* status TLV: the reference's own encoders (status.c) in the order radio_status.c:171-205 uses them, for
+ * the fields the product computes. types[] carries the enum status_type values (the caller reads them from status.h). */
+#include "status.h"
+int ref_glue_status(int demod_type, int isb, float noise_bw, float if_power, float bb_power, float gain, float pdev,
+                    float foffset, float snr, int channels, unsigned char *out) {
+  unsigned char *bp = out;
+  encode_float(&bp, NOISE_BANDWIDTH, noise_bw);
+  encode_float(&bp, IF_POWER, if_power);
+  encode_float(&bp, BASEBAND_POWER, bb_power);
+  encode_byte(&bp, DEMOD_MODE, demod_type);
+  switch (demod_type) {
+  case AM_DEMOD:
+    encode_float(&bp, DEMOD_GAIN, gain);
+    break;
+  case FM_DEMOD:
+    encode_float(&bp, PEAK_DEVIATION, pdev);
+    encode_float(&bp, FREQ_OFFSET, foffset);
+    encode_float(&bp, DEMOD_SNR, snr);
+    break;
+  default:
+    encode_float(&bp, DEMOD_GAIN, gain);
+    encode_int32(&bp, INDEPENDENT_SIDEBAND, isb);
+    break;
+  }
+  encode_int32(&bp, OUTPUT_CHANNELS, channels);
+  encode_eol(&bp);
+  return (int)(bp - out);
+}

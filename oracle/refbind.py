@@ -92,6 +92,7 @@ def lib():
     L.ref_glue_ingest.restype = C.c_longlong
     L.ref_glue_ingest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ref_glue_send.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.ref_glue_status.argtypes = [C.c_int, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_void_p]
     L.ref_hb15.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.ref_hb3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.ref_make_kaiser.argtypes = [C.c_void_p, C.c_uint, C.c_float]
@@ -332,3 +333,11 @@ def glue_send(channels: int, state: dict, samples: np.ndarray):
         pk.append(out[off:off + lens[i]].tobytes())
         off += int(lens[i])
     return pk
+
+
+def glue_status(demod_type: int, isb: int, noise_bw: float, if_power: float, bb_power: float, gain: float, pdev: float,
+                foffset: float, snr: float, channels: int) -> bytes:
+    """The reference's status.c encoders applied in radio_status.c's order to the fields the product computes."""
+    out = np.zeros(256, dtype=np.uint8)
+    n = lib().ref_glue_status(demod_type, isb, noise_bw, if_power, bb_power, gain, pdev, foffset, snr, channels, _ptr(out))
+    return out[:n].tobytes()

@@ -168,3 +168,45 @@ def test_packetiser_rejects_bad_arguments():
     o = rtp.PcmOut(1)
     with pytest.raises(ValueError):
         o.packetise(np.zeros(10, dtype=np.int16), 3)
+
+
+def test_status_tlv_matches_reference_encoders(ref):
+    """ka9q_status_encode_signals against status.c's encode_float / encode_byte / encode_int32 / encode_eol called in
+    radio_status.c's order (leading-zero suppression included: 0.0 encodes with length 0, small ints with one byte)."""
+    import ctypes as C
+    from ka9q_sdr_b200 import _lib
+    L = _lib.lib()
+    L.ka9q_status_encode_signals.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(5)
+    buf = (C.c_ubyte * 128)()
+    for demod_type in (0, 1, 2):
+        for trial in range(20):
+            st = _lib.ChanStatus()
+            vals = rng.standard_normal(6).astype(np.float32) * np.float32(10.0) ** rng.integers(-6, 6)
+            if trial == 0:
+                vals[:] = 0                      # every float suppressed to zero length
+            if trial == 1:
+                vals[:] = np.float32(np.nan)
+            st.bb_power, st.snr, st.foffset, st.pdeviation, st.agc_gain = (float(v) for v in vals[:5])
+            isb, nch = int(trial % 2), 1 + int(trial % 2)
+            ifp, nbw = float(vals[5]), float(np.float32(trial * 1234.5))
+            n = L.ka9q_status_encode_signals(C.byref(st), demod_type, isb, ifp, nbw, nch, buf, 128)
+            want = ref.glue_status(demod_type, isb, nbw, ifp, st.bb_power, st.agc_gain, st.pdeviation, st.foffset, st.snr, nch)
+            assert n == len(want) and bytes(buf[:n]) == want, (demod_type, trial)
+    assert L.ka9q_status_encode_signals(C.byref(st), 2, 0, 1.0, 1.0, 1, buf, 3) == -1      # no room
+
+
+def test_status_type_numbers_match_the_reference_header():
+    import os
+    import re
+    hdr = "/root/reference/status.h"
+    if not os.path.exists(hdr):
+        pytest.skip("reference tree not present")
+    txt = open(hdr).read()
+    body = re.sub(r"//.*", "", txt[txt.index("enum status_type {"):txt.index("};", txt.index("enum status_type {"))])
+    names = [n.strip().split("=")[0].strip() for n in body.split("{")[1].split(",") if n.strip()]
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ka9q_sdr_b200", "csrc", "rtp_glue.c")).read()
+    for name in ("NOISE_BANDWIDTH", "IF_POWER", "BASEBAND_POWER", "DEMOD_MODE", "INDEPENDENT_SIDEBAND", "DEMOD_SNR",
+                 "DEMOD_GAIN", "FREQ_OFFSET", "PEAK_DEVIATION", "OUTPUT_CHANNELS", "EOL"):
+        m = re.search(rf"ST_{name} = (\d+)", src)
+        assert m and int(m.group(1)) == names.index(name), name
