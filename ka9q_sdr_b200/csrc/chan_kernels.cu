@@ -28,18 +28,6 @@ namespace k9 {
 #define FM_CARVEOUT_PCT 70
 #endif
 
-struct CtaShared {
-  float2 buf[NDEC];   // FFT exchange buffer; afterwards the olen kept samples y[0..olen)
-  float aux0[1024];   // FM: audio of channel A / AM,linear: amplitude
-  float aux1[1024];   // FM: audio of channel B / AM: output / linear: per-sample gain
-  float red[16];
-  unsigned good[32];
-  float scal[8];
-  int ephase[2];      // (k * block_start) mod N per channel of the work item
-  ChanParams P[2];
-  ChanState S[2];
-};
-
 // FM pairs keep no audio on chip: the discriminator appends its output straight to the channel's audio-history ring in
 // global memory (it has to land there anyway, fm.c:162 / filter.c:164), and the audio transform reads the whole 2048
 // sample window back from the ring (L1/L2 hits). 16.8 KB per CTA: 8 CTAs fit the 164 KB carve-out, which leaves
@@ -92,53 +80,24 @@ __device__ __forceinline__ float2 load_bin(const float2* __restrict__ X, int N, 
   return __ldg(X + idx);
 }
 
-// Rolled (code-size matters more than unrolling here: the unrolled variant pushed the kernel past the instruction
-// cache and made instruction fetch the top stall): stage Y into the shared buffer in natural order, p = t + 128k.
-template <bool ISB>
-__device__ __forceinline__ void stage_filtered(const float2* __restrict__ X, int N, int bin,
-                                               const float2* __restrict__ H, float2* __restrict__ buf) {
+// ISB (CROSS_CONJ, filter.c:239-249): Y[p] = pos + conj(neg), Y[N_dec - p] = neg - conj(pos), staged into the shared buffer
+// in natural order, p = t + 128k (rolled: every element needs its mirror bin as well).
+__device__ __forceinline__ void stage_filtered_isb(const float2* __restrict__ X, int N, int bin,
+                                                   const float2* __restrict__ H, float2* __restrict__ buf) {
   const int t = threadIdx.x;
-  if (!ISB) {
-    // two halves of 8 elements; within a half the spectrum index just steps by 128 (one wrap test each), and all 16
-    // loads of the half are in flight before the first product is formed
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-      // half 0: p = t + 128k (k<8) -> s = p;  half 1: p = t + 1024 + 128k -> s = p - 2048, except p == 1024 (s = +1024)
-      int idx = bin + t + (half ? -1024 : 0);
-      if (idx < 0) idx += N;
-      if (idx >= N) idx -= N;
-      float2 x[8], h[8];
-      const float2* Hp = H + t + 1024 * half;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        int i = idx + 128 * k;
-        if (i >= N) i -= N;
-        if (half && k == 0 && t == 0) {  // the Nyquist bin belongs to the positive side (filter.c:206: p <= N_dec/2)
-          i = bin + 1024;
-          if (i >= N) i -= N;
-        }
-        x[k] = __ldg(X + i);
-        h[k] = __ldg(Hp + 128 * k);
-      }
-      float2* bp = buf + t + 1024 * half;
-#pragma unroll
-      for (int k = 0; k < 8; k++) bp[128 * k] = cmul(h[k], x[k]);
-    }
-  } else {
 #pragma unroll 2
-    for (int k = 0; k < 16; k++) {
-      const int p = t + 128 * k;
-      float2 y = cmul(__ldg(H + p), load_bin(X, N, bin, p));
-      if (p != 0 && p != NDEC / 2) {
-        const int pm = NDEC - p;
-        const float2 ym = cmul(__ldg(H + pm), load_bin(X, N, bin, pm));
-        if (p < NDEC / 2)
-          y = make_float2(y.x + ym.x, y.y - ym.y);  // pos + conj(neg)
-        else
-          y = make_float2(y.x - ym.x, y.y + ym.y);  // neg - conj(pos)
-      }
-      buf[p] = y;
+  for (int k = 0; k < 16; k++) {
+    const int p = t + 128 * k;
+    float2 y = cmul(__ldg(H + p), load_bin(X, N, bin, p));
+    if (p != 0 && p != NDEC / 2) {
+      const int pm = NDEC - p;
+      const float2 ym = cmul(__ldg(H + pm), load_bin(X, N, bin, pm));
+      if (p < NDEC / 2)
+        y = make_float2(y.x + ym.x, y.y - ym.y);  // pos + conj(neg)
+      else
+        y = make_float2(y.x - ym.x, y.y + ym.y);  // neg - conj(pos)
     }
+    buf[p] = y;
   }
 }
 
@@ -216,31 +175,11 @@ __device__ __forceinline__ int phase_advance(int e, int step, int N) {
   return e >= N ? e - N : e;
 }
 
-// (generic variant, reading back from the buffer) After the inverse transform: this thread's partial sums of |y|^2 and |y| and
-// its minimum |y|^2 over the kept samples n in [first, NDEC). Each thread reads only the elements it stored itself
-// (n = t + 128j), so no barrier is needed between store16 and this. The per-block LO phase (Appendix C) is NOT applied
-// here: |y| does not depend on it; the consumers that do (discriminator state across blocks, linear output, the debug
-// capture) apply it themselves, once per block or fused into a multiply they already do.
-__device__ __forceinline__ void kept_stats(const float2* __restrict__ buf, int first, float* sumsq, float* sumamp,
-                                           float* minsq) {
-  float ssq = 0.f, samp = 0.f, mn = INFINITY;
-#pragma unroll 4
-  for (int n = threadIdx.x + 128 * (first >> 7); n < NDEC; n += 128) {
-    if (n >= first) {
-      const float2 y = buf[n];
-      const float q = y.x * y.x + y.y * y.y;
-      ssq += q;
-      mn = fminf(mn, q);
-      // |y| for the squelch statistics only (fm.c:95): MUFU.RSQ based, ~1 ulp; it only feeds threshold decisions
-      samp += (q > 0.f) ? q * rsqrtf(q) : 0.f;
-    }
-  }
-  *sumsq = ssq;
-  *sumamp = samp;
-  *minsq = mn;
-}
-
-// store16 + kept_stats in one pass over the registers (rows j >= jb only; the row j == jb is partly history)
+// After the inverse transform: store the kept rows (j >= jb; the row j == jb is partly history) for the discriminator and,
+// in the same pass over the registers, this thread's partial sums of |y|^2 and |y| and its minimum |y|^2 over the kept
+// samples n in [first, NDEC). The per-block LO phase (Appendix C) is NOT applied here: |y| does not depend on it; the
+// consumers that do (discriminator state across blocks, linear output, the debug capture) apply it themselves, once per
+// block or fused into a multiply they already do.
 __device__ __forceinline__ void store16_stats(const float2 (&v)[16], float2* __restrict__ buf, int first, float* sumsq,
                                               float* sumamp, float* minsq) {
   const int t = threadIdx.x;
@@ -666,7 +605,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
       const int bin = (int)a.params[c].bin;
       const bool isb = LINEAR && (a.params[c].flags & CH_ISB);
       if (isb) {  // CTA-uniform; the mirror-bin fold is staged through shared memory
-        stage_filtered<true>(X, a.N, bin, a.resp + (long long)c * NDEC, sh.buf);
+        stage_filtered_isb(X, a.N, bin, a.resp + (long long)c * NDEC, sh.buf);
         __syncthreads();
         load16(v, sh.buf);
       } else {
@@ -888,7 +827,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 8) agc_front_kernel(const Cha
   for (int b = 0; b < a.nblocks; b++) {
     const float2* X = a.spec + (long long)b * a.spec_stride;
     if (isb) {  // CTA-uniform; the mirror-bin fold is staged through shared memory
-      stage_filtered<true>(X, a.N, bin, H, sh.buf);
+      stage_filtered_isb(X, a.N, bin, H, sh.buf);
       __syncthreads();
       load16(v, sh.buf);
     } else {
