@@ -6,6 +6,7 @@
 //   even_samples[1..3] = x[-2], x[-4], x[-6]; odd_samples[1..3] = x[-1], x[-3], x[-5];
 //   old_odd_samples[3..0] = x[-7], x[-9], x[-11], x[-13]   (indices relative to the next call's x[0]).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "../../include/ka9q_b200.h"
@@ -35,6 +36,78 @@ __global__ void hb3_kernel(const float* __restrict__ x, float prev, float* __res
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < cnt; m += gridDim.x * blockDim.x) {
     const float xm1 = m > 0 ? x[2 * m - 1] : prev;
     y[m] = 2 * x[2 * m] + x[2 * m + 1] + xm1;
+  }
+}
+
+// Whole cascade in one launch (stages <= 6, the hackrf /64 case): each CTA produces FUSED_C final outputs and recomputes
+// the halo it needs at every level in shared memory (out[m] needs in[2m-13 .. 2m+1], so a chunk [a, b) of a level's
+// output needs [2a-13, 2b) of its input). Level l = 0 is the highest rate; its state is states[S-1-l]
+// (hackrf.c:297-301). Samples at negative indices of a level come from that level's carried history, exactly as in the
+// per-stage kernel, and every output is formed by the same expression, so the result is bit-identical.
+constexpr int FUSED_MAXS = 6;
+constexpr int FUSED_C = 64;
+constexpr int FUSED_BUF = (FUSED_C << FUSED_MAXS) + 13 * ((1 << FUSED_MAXS) - 1) + 8;
+
+struct FusedArgs {
+  const float* x;     // level-0 input, n_in samples
+  const float* hist;  // [S][16]: hist[l][k] = x_l[-k], k = 1..13
+  float4 coeff[FUSED_MAXS];
+  int S, n_in;
+  float* y;     // n_in >> S outputs
+  float* tail;  // [S][16]: tail[l][k] = last samples of (history ++ input) of level l, k = 1..13
+};
+
+__global__ void __launch_bounds__(256) hb15_cascade_kernel(const FusedArgs a) {
+  __shared__ float buf[2][FUSED_BUF];
+  __shared__ float hs[FUSED_MAXS][16];
+  const int t = threadIdx.x;
+  const int S = a.S;
+  if (t < 16 * S) hs[t >> 4][t & 15] = a.hist[t];
+  const int n_out = a.n_in >> S;
+  const int m0 = blockIdx.x * FUSED_C, m1 = min(m0 + FUSED_C, n_out);
+  const bool last_cta = m1 == n_out;
+  // needed range of every level's input, from the final outputs back to level 0
+  int lo[FUSED_MAXS + 1], hi[FUSED_MAXS + 1];
+  lo[S] = m0;
+  hi[S] = m1;
+  for (int l = S - 1; l >= 0; l--) {
+    lo[l] = 2 * lo[l + 1] - 13;
+    hi[l] = 2 * hi[l + 1];
+  }
+  // level 0 from global memory; buffer slot i - lo[l] holds sample i of level l (i >= 0 only)
+  for (int i = max(lo[0], 0) + t; i < hi[0]; i += blockDim.x) buf[0][i - lo[0]] = a.x[i];
+  __syncthreads();
+  int cur = 0;
+  for (int l = 0; l < S; l++) {
+    const float* in = buf[cur];
+    float* out = buf[cur ^ 1];
+    const float* h = hs[l];
+    const int lo_in = lo[l];
+    auto X = [&](int i) -> float { return i >= 0 ? in[i - lo_in] : h[-i]; };
+    if (last_cta && t < 16) {  // new state of this level: the last 13 samples of (history ++ input)
+      const int n_l = a.n_in >> l;
+      if (t >= 1 && t <= 13) {
+        const int i = n_l - t;
+        a.tail[16 * l + t] = i >= 0 ? in[i - lo_in] : h[t - n_l];
+      }
+    }
+    const float4 c = a.coeff[l];
+    const bool final_level = l == S - 1;
+    for (int m = max(lo[l + 1], 0) + t; m < hi[l + 1]; m += blockDim.x) {
+      const int b = 2 * m;
+      // same association as the portable reference loop: centre, then taps from the tails inwards (decimate.c:124-128)
+      float r = X(b - 6);
+      r += (X(b + 1) + X(b - 13)) * c.x;
+      r += (X(b - 1) + X(b - 11)) * c.y;
+      r += (X(b - 3) + X(b - 9)) * c.z;
+      r += (X(b - 5) + X(b - 7)) * c.w;
+      if (final_level)
+        a.y[m] = r;
+      else
+        out[m - lo[l + 1]] = r;
+    }
+    __syncthreads();
+    cur ^= 1;
   }
 }
 
@@ -145,6 +218,33 @@ int ka9q_hb15_cascade(int device, int stages, struct hb15_state* states, const f
   float* a = g_scr.d_a;
   float* b = g_scr.d_b;
   if (cudaMemcpy(a, in, sizeof(float) * n_in, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  if (stages <= FUSED_MAXS && !(getenv("KA9Q_B200_HB15_FUSED") && atoi(getenv("KA9Q_B200_HB15_FUSED")) == 0)) {
+    // one launch, one upload of all histories, one download of all tails
+    float hist[FUSED_MAXS * 16], tail[FUSED_MAXS * 16];
+    FusedArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    for (int l = 0; l < stages; l++) {
+      const struct hb15_state* st = &states[stages - 1 - l];
+      state_to_hist(st, hist + 16 * l);
+      fa.coeff[l] = make_float4(st->coeffs[0], st->coeffs[1], st->coeffs[2], st->coeffs[3]);
+    }
+    float* d_hist = g_scr.d_hist;            // [64][16] floats: histories in the first half, tails in the second
+    float* d_tail = g_scr.d_hist + 16 * 32;
+    if (cudaMemcpy(d_hist, hist, sizeof(float) * 16 * stages, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    fa.x = a;
+    fa.hist = d_hist;
+    fa.S = stages;
+    fa.n_in = n_in;
+    fa.y = b;
+    fa.tail = d_tail;
+    const int n_out = n_in >> stages;
+    hb15_cascade_kernel<<<(n_out + FUSED_C - 1) / FUSED_C, 256>>>(fa);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    if (cudaMemcpy(out, b, sizeof(float) * n_out, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (cudaMemcpy(tail, d_tail, sizeof(float) * 16 * stages, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int l = 0; l < stages; l++) hist_to_state(&states[stages - 1 - l], tail + 16 * l);
+    return 0;
+  }
   int n = n_in;
   // highest-rate stage first: stage index stages-1 down to 0, each with its own state (hackrf.c:297-301)
   for (int j = stages - 1; j >= 0; j--) {

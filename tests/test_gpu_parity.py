@@ -522,3 +522,24 @@ def test_halfband_decimators_match_golden_and_reference(ref):
     got16 = np.round(32767 * out * atten).astype(np.int32)
     want16 = np.round(32767 * buf * atten).astype(np.int32)
     assert np.abs(got16 - want16).max() <= 1
+    # second chunk: the six carried states; and the fused one-launch cascade against the stage-by-stage form, bit for bit
+    sig2 = (0.3 * np.sin(2 * np.pi * 0.0007 * (n + np.arange(n))) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    out2 = np.zeros(n // 64, dtype=np.float32)
+    assert lib.ka9q_hb15_cascade(0, 6, states, sig2.ctypes.data_as(C.c_void_p), n, out2.ctypes.data_as(C.c_void_p)) == 0
+    buf = sig2.copy()
+    for j in range(5, -1, -1):
+        buf = ref.hb15(rstates[j], buf)
+    assert np.abs(np.round(32767 * out2 * atten) - np.round(32767 * buf * atten)).max() <= 1
+    os.environ["KA9Q_B200_HB15_FUSED"] = "0"
+    try:
+        st2 = (_lib.Hb15State * 6)()
+        for j in range(6):
+            for i in range(4):
+                st2[j].coeffs[i] = coeffs[i]
+        o1, o2 = np.zeros(n // 64, dtype=np.float32), np.zeros(n // 64, dtype=np.float32)
+        assert lib.ka9q_hb15_cascade(0, 6, st2, sig.ctypes.data_as(C.c_void_p), n, o1.ctypes.data_as(C.c_void_p)) == 0
+        assert lib.ka9q_hb15_cascade(0, 6, st2, sig2.ctypes.data_as(C.c_void_p), n, o2.ctypes.data_as(C.c_void_p)) == 0
+    finally:
+        del os.environ["KA9Q_B200_HB15_FUSED"]
+    assert np.array_equal(o1, out) and np.array_equal(o2, out2)
+    assert bytes(st2) == bytes(states)
