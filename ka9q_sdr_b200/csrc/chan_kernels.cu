@@ -32,8 +32,24 @@ namespace k9 {
 // global memory (it has to land there anyway, fm.c:162 / filter.c:164), and the audio transform reads the whole 2048
 // sample window back from the ring (L1/L2 hits). 16.8 KB per CTA: 8 CTAs fit the 164 KB carve-out, which leaves
 // ~90 KB of L1 for the spectrum windows that neighbouring channels share and the twiddle / de-emphasis tables.
+// FM_TMA: spectrum windows staged by the TMA unit (1-D bulk copy, cp.async.bulk + mbarrier: UBLKCP in SASS) instead of
+// sixteen 64-bit loads per thread. 0 = register-direct loads (LDG); 1 = bulk copy into the FFT exchange buffer itself
+// (no extra shared memory, the copy's latency is exposed to the CTA and covered by the other CTAs of the SM);
+// 2 = bulk copy into a dedicated landing buffer, issued one channel-job ahead so it lands under the previous job's
+// transform (33 KB per CTA: 6 CTAs per SM). Measured A/B: DESIGN.md section 3.
+#ifndef FM_TMA
+#define FM_TMA 0
+#endif
+constexpr int TMA_WIN = NDEC + 2;  // the copy starts on an even bin (16-byte aligned source): 2050 bins cover any window
+
 struct FmShared {
-  float2 buf[NDEC];  // FFT exchange buffer; afterwards the olen kept samples y[0..olen)
+  alignas(16) float2 buf[FM_TMA == 1 ? TMA_WIN : NDEC];  // FFT exchange buffer; afterwards the olen kept samples y[0..olen)
+#if FM_TMA == 2
+  alignas(16) float2 land[TMA_WIN];  // landing buffer of the prefetched spectrum window
+#endif
+#if FM_TMA
+  alignas(8) unsigned long long tma_bar;  // mbarrier the bulk copy completes on
+#endif
   float red[16], red2[16];  // one scratch row per reduction of a channel-block: no barrier needed to recycle them
   unsigned good[32];
   float scal[8];
@@ -155,6 +171,60 @@ __device__ __forceinline__ void load_filtered16(float2 (&v)[16], const float2* _
 #pragma unroll
     for (int r = 0; r < 8; r++) v[8 * e + r] = cmul(__ldg(Hp + 128 * (e + 2 * r)), v[8 * e + r]);
 }
+#if FM_TMA
+// ---- TMA-staged window (cp.async.bulk: global -> shared, completion on an mbarrier) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// the whole 2048-bin window of a channel lies inside [0, N) together with the alignment pad (all but the band-edge channels)
+__device__ __forceinline__ bool tma_window_inside(int bin, int N) { return bin >= 1024 && bin + 1026 <= N; }
+// one elected thread: order the CTA's earlier generic-proxy accesses to dst before the async-proxy write, arm the
+// barrier with the byte count and start the copy of bins [start, start + 2050), start = (bin - 1023) rounded down to even
+__device__ __forceinline__ void tma_issue_window(float2* dst, const float2* __restrict__ X, int bin, unsigned long long* bar) {
+  const int start = (bin - 1023) & ~1;
+  const unsigned bytes = TMA_WIN * sizeof(float2);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(X + start), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// staged window -> transform input registers, times the response: row j = e + 2r of thread t is FFT index p = t + 128 j;
+// p <= 1024 is bin + p (G[p + 1023 + off]), p > 1024 is bin + p - 2048 (G[p - 1025 + off]); off = 0 / 1 from the alignment
+__device__ __forceinline__ void load_filtered16_staged(float2 (&v)[16], const float2* __restrict__ G, int bin,
+                                                       const float2* __restrict__ H) {
+  const int t = threadIdx.x;
+  const int off = (bin - 1023) & 1;
+  const float2* gp = G + t + 1023 + off;  // rows 0..7
+  const float2* gn = G + t - 1025 + off;  // rows 9..15 (+128 j); row 8: Nyquist for t == 0
+#pragma unroll
+  for (int e = 0; e < 2; e++)
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int j = e + 2 * r;
+      v[8 * e + r] = j < 8 ? gp[128 * j] : (j == 8 ? (t ? gn[1024] : gp[1024]) : gn[128 * j]);
+    }
+  const float2* Hp = H + t;
+#pragma unroll
+  for (int e = 0; e < 2; e++)
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[8 * e + r] = cmul(__ldg(Hp + 128 * (e + 2 * r)), v[8 * e + r]);
+}
+#endif
+
 // transform output -> buffer in natural order: buf[t + 128j] = v[j], only the rows that hold kept samples (j >= jb)
 __device__ __forceinline__ void store16(const float2 (&v)[16], float2* __restrict__ buf, int jb) {
   float2* bp = buf + threadIdx.x;
@@ -354,7 +424,11 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, con
   float new_last = 0.f, foffset = sh.S[h].fm_foffset, pdeviation = sh.S[h].fm_pdeviation;
   if (open) {
     const float min_ampl = 0.55f * 0.55f * avg_amp * avg_amp;  // fm.c:121
-    const float2 old_state = cmul(sh.S[h].fm_state, ph);       // into this block's unrotated domain
+    // into this block's unrotated domain. A carried state of exactly (0,0) (the squelch was shut, fm.c:156) stays
+    // (+0,+0): the rotation would hand atan2 other zero signs than the reference's cargf(samp * 0) sees, and the first
+    // audio sample after the squelch re-opens is 0 or +-pi depending on exactly those signs.
+    const float2 st0 = sh.S[h].fm_state;
+    const float2 old_state = (st0.x == 0.f && st0.y == 0.f) ? make_float2(0.f, 0.f) : cmul(st0, ph);
     const float old_last = sh.S[h].fm_lastaudio;
     const bool all_good = minsq > min_ampl;  // every sample passes the blanking threshold (the usual case)
     dbg_allgood = all_good ? 1.f : 0.f;
@@ -454,11 +528,23 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
       sh.ephase[t] = phase_index0(sh.P[t].bin, a.start0, a.N);
     }
   }
+#if FM_TMA
+  if (t == 0) mbar_init(&sh.tma_bar, 1);
+  unsigned tma_phase = 0;
+#endif
   __syncthreads();
   const int olen = OLEN_T ? OLEN_T : a.olen;
   const int first = NDEC - olen;
   const int jb = first >> 7, rem = first & 127;
   const bool filtered = sh.P[0].audio_slot >= 0;
+#if FM_TMA
+  // CTA-uniform: every window of the work item lies inside [0, N) (band-edge channels take the LDG path, which wraps)
+  const bool use_tma = tma_window_inside((int)sh.P[0].bin, a.N) && (wk.y < 0 || tma_window_inside((int)sh.P[1].bin, a.N));
+#endif
+#if FM_TMA == 2
+  // prefetch pipeline: the window of the next channel-job is copied while the current one is transformed
+  if (t == 0 && a.nblocks > 0 && use_tma) tma_issue_window(sh.land, a.spec, (int)sh.P[0].bin, &sh.tma_bar);
+#endif
   // Audio-history rings of the pair (2048 floats each). An absent channel B reads the spare all-zero ring that follows
   // the last channel's; nothing is ever written to it.
   float* const histA = a.audio_hist + (long long)wk.x * NDEC;
@@ -480,7 +566,29 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
       const int c = h ? wk.y : wk.x;
       if (job < 2) {
         if (c < 0) continue;
-        load_filtered16(v, X, a.N, (int)sh.P[h].bin, a.resp + (long long)c * NDEC);
+#if FM_TMA == 1
+        if (use_tma) {
+          __syncthreads();  // every earlier reader / writer of the exchange buffer is done
+          if (t == 0) tma_issue_window(sh.buf, X, (int)sh.P[h].bin, &sh.tma_bar);
+          mbar_wait(&sh.tma_bar, tma_phase);
+          tma_phase ^= 1;
+          load_filtered16_staged(v, sh.buf, (int)sh.P[h].bin, a.resp + (long long)c * NDEC);
+        } else
+#elif FM_TMA == 2
+        if (use_tma) {
+          mbar_wait(&sh.tma_bar, tma_phase);
+          tma_phase ^= 1;
+          load_filtered16_staged(v, sh.land, (int)sh.P[h].bin, a.resp + (long long)c * NDEC);
+          __syncthreads();  // the landing buffer has been read by everybody: start the next window's copy
+          if (t == 0) {
+            if (h == 0 && wk.y >= 0)
+              tma_issue_window(sh.land, X, (int)sh.P[1].bin, &sh.tma_bar);
+            else if (b + 1 < a.nblocks)
+              tma_issue_window(sh.land, X + a.spec_stride, (int)sh.P[0].bin, &sh.tma_bar);
+          }
+        } else
+#endif
+          load_filtered16(v, X, a.N, (int)sh.P[h].bin, a.resp + (long long)c * NDEC);
       } else if (job == 2) {
         if (!filtered) break;
         // Two real channels ride one complex transform, z = audA + j audB (the filter's impulse response is real),
@@ -497,7 +605,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
           }
       }
       // the buffer's previous readers are a barrier behind us except after job 2 (its last stage just read it)
-      fft2048<+1>(v, sh.buf, a.tw2048, !FM_FEWER_BARRIERS || job == 3);
+      fft2048<+1>(v, sh.buf, a.tw2048, !FM_FEWER_BARRIERS || job == 3 || (FM_TMA == 1 && job < 2));
       if (job < 2) {
         float ssq, samp, minsq;
         const int e = sh.ephase[h];
@@ -1048,7 +1156,7 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
           const bool over = x * gain > headroom;
           const float kept = hang != 0 ? gain : gain * rf;  // hold, or recover
           gain = over ? q : kept;
-          hang = over ? hangmax : max(hang - 1, 0);
+          hang = over ? hangmax : (hang != 0 ? hang - 1 : 0);  // am.c:68-69 / linear.c:275-276, also for hangmax < 0
           return gain;
         };
         int i0 = 0;

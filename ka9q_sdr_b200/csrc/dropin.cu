@@ -137,6 +137,8 @@ struct filter_in* create_filter_input(unsigned int const L, unsigned int const M
   if (bigfft_plan_create(&m->plan, N) != 0) {
     set_error("create_filter_input: FFT size %d has no supported factorisation", N);
     fprintf(stderr, "ka9q_b200: %s\n", get_error());
+    pthread_mutex_destroy(&m->pub.filter_mutex);
+    pthread_cond_destroy(&m->pub.filter_cond);
     free(m);
     return NULL;
   }
@@ -156,6 +158,7 @@ struct filter_in* create_filter_input(unsigned int const L, unsigned int const M
   if (!ok) {
     set_error("create_filter_input: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     fprintf(stderr, "ka9q_b200: %s\n", get_error());
+    delete_filter_input(&m->pub);  // frees the plan, the host mirrors and whatever device buffers were obtained
     return NULL;
   }
   return &m->pub;
@@ -208,7 +211,9 @@ struct filter_out* create_filter_output(struct filter_in* master, void* response
   ok = ok && cudaMalloc(&s->d_tmp0, sizeof(float2) * N_dec) == cudaSuccess;
   ok = ok && cudaMalloc(&s->d_tmp1, sizeof(float2) * N_dec) == cudaSuccess;
   if (!ok) {
-    set_error("create_filter_output: device allocation failed");
+    set_error("create_filter_output: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    s->pub.response = NULL;  // the caller keeps its response on failure
+    delete_filter_output(&s->pub);
     return NULL;
   }
   return &s->pub;
@@ -308,13 +313,15 @@ int delete_filter_input(struct filter_in* const master) {
   if (master == NULL) return 0;
   InPriv* m = (InPriv*)master;
   cudaSetDevice(m->device);
-  cudaStreamSynchronize(m->st);
+  if (m->st) cudaStreamSynchronize(m->st);
   bigfft_plan_destroy(&m->plan);
   cudaFree(m->d_ring);
   cudaFree(m->d_fdomain);
   cudaFree(m->d_tmp0);
   cudaFree(m->d_tmp1);
-  cudaStreamDestroy(m->st);
+  if (m->st) cudaStreamDestroy(m->st);
+  pthread_mutex_destroy(&master->filter_mutex);
+  pthread_cond_destroy(&master->filter_cond);
   ka9q_free(master->input_buffer.r);
   ka9q_free(master->fdomain);
   free(m);

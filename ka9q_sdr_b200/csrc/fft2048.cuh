@@ -25,11 +25,19 @@ namespace k9 {
 
 constexpr int FFT2048_THREADS = 128;
 
-// Twiddle table layout (FFT2048_TW_FLOAT2 float2 entries, built by fft2048_fill_twiddles on the host):
-//   [8p + j], p in [0,256), j in [0,8):   W_2048^(p*j)        stage-1 rows, one 64-byte row per butterfly
-//   [2048 + 16p' + j], p' in [0,16), j in [0,16): W_256^(p'*j) stage-2 rows, one 128-byte row per thread
-// Forward sign (exp(-2*pi*i...)); conjugated on use when SIGN=+1. Rows are read with 128-bit loads.
-constexpr int FFT2048_TW_FLOAT2 = 2048 + 256;
+// Twiddle table layout (FFT2048_TW_FLOAT2 float2 entries, built by fft2048_fill_twiddles on the host), laid out so that
+// the lanes of a warp read CONSECUTIVE addresses (the L1 data pipe was the kernel's limiter, and a row per thread costs
+// one wavefront per lane: ncu round 1, 2560 of 7230 wavefronts per FM pair-block were twiddle rows):
+//   stage 1, butterfly p in [0,256), twiddles W_2048^(p*j), j = 1..7 (j = 0 is 1 and is not stored):
+//     float4 A[jj][p], jj in [0,3): (W^(p(2jj+1)), W^(p(2jj+2)))      at float2 offset 2*(256*jj + p)
+//     float2 B[p]:                   W^(7p)                           at float2 offset 1536 + p
+//   stage 2, butterfly p' = t >> 3 in [0,16), twiddles W_256^(p'*j), j = 0..15: the four p' of a warp side by side,
+//     float4 C[w][jj][sub], p' = 4w + sub: (W^(p'*2jj), W^(p'*(2jj+1)))  at float2 offset 1792 + 2*((8w + jj)*4 + sub)
+//     (a warp's 128-bit load touches one 64-byte segment)
+// Forward sign (exp(-2*pi*i...)); conjugated on use when SIGN=+1. Same values and the same arithmetic as a row-per-
+// thread table: results are bit-identical.
+constexpr int FFT2048_TW_FLOAT2 = 1792 + 256;
+constexpr int FFT2048_TW_B = 1536, FFT2048_TW_C = 1792;
 
 template <int SIGN>
 __device__ __forceinline__ float2 tw_mul(float2 a, float wx, float wy) {
@@ -45,13 +53,15 @@ __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb
 #pragma unroll
   for (int e = 0; e < 2; e++) {
     Dft<8, SIGN>::run(&v[8 * e]);
-    const float4* row = reinterpret_cast<const float4*>(tw + 8 * (t + 128 * e));
+    const float4* A = reinterpret_cast<const float4*>(tw) + (t + 128 * e);
 #pragma unroll
-    for (int jj = 0; jj < 4; jj++) {
-      const float4 w = __ldg(row + jj);
-      if (jj > 0) v[8 * e + 2 * jj] = tw_mul<SIGN>(v[8 * e + 2 * jj], w.x, w.y);
-      v[8 * e + 2 * jj + 1] = tw_mul<SIGN>(v[8 * e + 2 * jj + 1], w.z, w.w);
+    for (int jj = 0; jj < 3; jj++) {
+      const float4 w = __ldg(A + 256 * jj);
+      v[8 * e + 2 * jj + 1] = tw_mul<SIGN>(v[8 * e + 2 * jj + 1], w.x, w.y);
+      v[8 * e + 2 * jj + 2] = tw_mul<SIGN>(v[8 * e + 2 * jj + 2], w.z, w.w);
     }
+    const float2 w7 = __ldg(tw + FFT2048_TW_B + t + 128 * e);
+    v[8 * e + 7] = tw_mul<SIGN>(v[8 * e + 7], w7.x, w7.y);
   }
   if (war_sync) __syncthreads();  // WAR: previous users of the buffer are done (CTA-uniform flag)
   {
@@ -75,10 +85,10 @@ __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb
   }
   Dft<16, SIGN>::run(v);
   {
-    const float4* row = reinterpret_cast<const float4*>(tw + 2048 + 16 * (t >> 3));
+    const float4* row = reinterpret_cast<const float4*>(tw + FFT2048_TW_C) + 32 * (t >> 5) + ((t >> 3) & 3);
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) {
-      const float4 w = __ldg(row + jj);
+      const float4 w = __ldg(row + 4 * jj);
       if (jj > 0) v[2 * jj] = tw_mul<SIGN>(v[2 * jj], w.x, w.y);
       v[2 * jj + 1] = tw_mul<SIGN>(v[2 * jj + 1], w.z, w.w);
     }
@@ -109,15 +119,22 @@ __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb
 // Host-side table builder (double precision, rounded once)
 inline void fft2048_fill_twiddles(float2* tw) {
   const double pi = 3.14159265358979323846;
-  for (int p = 0; p < 256; p++)
-    for (int j = 0; j < 8; j++) {
-      const double ang = -2.0 * pi * (double)((p * j) % 2048) / 2048.0;
-      tw[8 * p + j] = make_float2((float)cos(ang), (float)sin(ang));
+  auto w = [&](int num, int den) {
+    const double ang = -2.0 * pi * (double)(num % den) / (double)den;
+    return make_float2((float)cos(ang), (float)sin(ang));
+  };
+  for (int p = 0; p < 256; p++) {
+    for (int jj = 0; jj < 3; jj++) {
+      tw[2 * (256 * jj + p)] = w(p * (2 * jj + 1), 2048);
+      tw[2 * (256 * jj + p) + 1] = w(p * (2 * jj + 2), 2048);
     }
+    tw[FFT2048_TW_B + p] = w(p * 7, 2048);
+  }
   for (int pp = 0; pp < 16; pp++)
-    for (int j = 0; j < 16; j++) {
-      const double ang = -2.0 * pi * (double)((pp * j) % 256) / 256.0;
-      tw[2048 + 16 * pp + j] = make_float2((float)cos(ang), (float)sin(ang));
+    for (int jj = 0; jj < 8; jj++) {
+      const int idx = FFT2048_TW_C + 2 * ((8 * (pp >> 2) + jj) * 4 + (pp & 3));
+      tw[idx] = w(pp * 2 * jj, 256);
+      tw[idx + 1] = w(pp * (2 * jj + 1), 256);
     }
 }
 

@@ -103,6 +103,18 @@ struct ka9q_stream {
   size_t ev_next = 0;
 };
 
+// NCCL entry points (libnccl is dlopen'ed on first use, see load_nccl)
+typedef struct ncclComm* k9_ncclComm_t;
+typedef struct {
+  char internal[128];
+} k9_ncclUniqueId;
+static int (*p_ncclGetUniqueId)(k9_ncclUniqueId*);
+static int (*p_ncclCommInitRank)(k9_ncclComm_t*, int, k9_ncclUniqueId, int);
+static int (*p_ncclBroadcast)(const void*, void*, size_t, int, int, k9_ncclComm_t, cudaStream_t);
+static int (*p_ncclCommDestroy)(k9_ncclComm_t);
+static int (*p_ncclAllGather)(const void*, void*, size_t, int, k9_ncclComm_t, cudaStream_t);
+static const char* (*p_ncclGetErrorString)(int);
+
 enum TimeClass { TC_FFT = 0, TC_FM = 1, TC_AM = 2, TC_LIN = 3, TC_BCAST = 4, TC_COUNT = 5 };
 
 static cudaEvent_t timing_event(ka9q_stream* s) {
@@ -315,6 +327,7 @@ int ka9q_stream_add_channel(ka9q_stream* s, const ka9q_chan_params* p) {
   K9_CHECK(p->demod_type >= 0 && p->demod_type <= 2, "bad demod_type");
   K9_CHECK(!(p->flags & (KA9Q_FLAG_PLL | KA9Q_FLAG_SQUARE)),
            "PLL / squaring carrier tracking (linear.c:129-246) is not implemented in this build");
+  K9_CHECK(!(p->hangtime < 0), "negative AGC hang time");
   K9_CHECK(!isnan(p->low) && !isnan(p->high), "filter edges must be set (set_filter returns -1 on NAN, filter.c:504)");
   ka9q_chan_params q = *p;
   if (q.low > q.high) std::swap(q.low, q.high);  // radio.c:347-353
@@ -327,10 +340,21 @@ int ka9q_stream_add_channel(ka9q_stream* s, const ka9q_chan_params* p) {
   return (int)s->chans.size() - 1;
 }
 
+static int commit_impl(ka9q_stream* s);
+static void release_resources(ka9q_stream* s);
+
 int ka9q_stream_commit(ka9q_stream* s) {
   K9_CHECK(s, "null argument");
   K9_CHECK(!s->committed, "already committed");
   K9_CHECK(!s->chans.empty(), "no channels");
+  if (commit_impl(s)) {
+    release_resources(s);  // nothing allocated so far outlives a failed commit (the error text is kept)
+    return -1;
+  }
+  return 0;
+}
+
+static int commit_impl(ka9q_stream* s) {
   K9_CUDA(cudaSetDevice(s->cfg.device));
   const int K = (int)s->chans.size();
   const int B = s->cfg.max_blocks;
@@ -787,7 +811,8 @@ int ka9q_stream_last_timing(ka9q_stream* s, float* total_ms, float* fft_ms, floa
 
 int ka9q_stream_spectrum_ptr(ka9q_stream* s, void** dev_ptr, long long* bytes_per_block) {
   K9_CHECK(s && s->committed, "stream not committed");
-  if (dev_ptr) *dev_ptr = spec_buf(s, s->spec_rd ^ 1);  // the buffer the last channel launch read
+  // the buffer compute_fft_only just wrote (not yet handed to the channel kernels), else the one the last launch read
+  if (dev_ptr) *dev_ptr = spec_buf(s, s->fft_pending ? s->spec_wr : (s->spec_rd ^ 1));
   if (bytes_per_block) *bytes_per_block = (long long)sizeof(float2) * s->N;
   return 0;
 }
@@ -796,6 +821,7 @@ int ka9q_stream_get_response(ka9q_stream* s, int chan, void* out2048, float* noi
   K9_CHECK(s && s->committed, "stream not committed");
   K9_CHECK(chan >= 0 && chan < (int)s->chans.size(), "bad channel");
   K9_CUDA(cudaSetDevice(s->cfg.device));
+  if (ka9q_stream_sync(s)) return -1;  // the work streams are non-blocking: order behind everything in flight
   if (out2048)
     K9_CUDA(cudaMemcpy(out2048, s->d_resp + (size_t)chan * NDEC, sizeof(float2) * NDEC, cudaMemcpyDeviceToHost));
   if (noise_gain) *noise_gain = s->h_noise_gain[chan];
@@ -806,6 +832,7 @@ int ka9q_stream_get_filter_output(ka9q_stream* s, int chan, int nblocks, void* o
   K9_CHECK(s && s->committed && s->d_filt, "filter-output capture not enabled");
   K9_CHECK(chan >= 0 && chan < (int)s->chans.size() && nblocks >= 1 && nblocks <= s->cfg.max_blocks, "bad argument");
   K9_CUDA(cudaSetDevice(s->cfg.device));
+  if (ka9q_stream_sync(s)) return -1;  // the work streams are non-blocking: order behind everything in flight
   const int K = (int)s->chans.size();
   K9_CUDA(cudaMemcpy2D(out, sizeof(float2) * s->olen, s->d_filt + (size_t)chan * s->olen, sizeof(float2) * (size_t)K * s->olen,
                        sizeof(float2) * s->olen, nblocks, cudaMemcpyDeviceToHost));
@@ -816,44 +843,67 @@ int ka9q_stream_get_spectrum(ka9q_stream* s, int block, void* outN) {
   K9_CHECK(s && s->committed, "stream not committed");
   K9_CHECK(block >= 0 && block < s->cfg.max_blocks, "bad block");
   K9_CUDA(cudaSetDevice(s->cfg.device));
-  K9_CUDA(cudaStreamSynchronize(s->s_fft));
-  K9_CUDA(cudaMemcpy(outN, spec_buf(s, s->spec_rd ^ 1) + (size_t)block * s->N, sizeof(float2) * s->N, cudaMemcpyDeviceToHost));
+  if (ka9q_stream_sync(s)) return -1;
+  K9_CUDA(cudaMemcpy(outN, spec_buf(s, s->fft_pending ? s->spec_wr : (s->spec_rd ^ 1)) + (size_t)block * s->N, sizeof(float2) * s->N, cudaMemcpyDeviceToHost));
   return 0;
 }
 
 int ka9q_stream_get_if_energy(ka9q_stream* s, int nblocks, float* energy) {
   K9_CHECK(s && s->committed && energy, "bad argument");
   K9_CUDA(cudaSetDevice(s->cfg.device));
+  if (ka9q_stream_sync(s)) return -1;  // the work streams are non-blocking: order behind everything in flight
   K9_CUDA(cudaMemcpy(energy, s->d_energy, sizeof(float) * nblocks, cudaMemcpyDeviceToHost));
   return 0;
 }
 
-int ka9q_stream_destroy(ka9q_stream* s) {
-  if (!s) return 0;
+// Frees every device / host / stream / event resource of a stream (idempotent). Used by destroy and by the failure paths
+// of commit, so a stream that could not be committed leaks nothing.
+static void release_resources(ka9q_stream* s) {
   cudaSetDevice(s->cfg.device);
   cudaDeviceSynchronize();
+  if (s->nccl_comm && p_ncclCommDestroy) p_ncclCommDestroy((k9_ncclComm_t)s->nccl_comm);
+  s->nccl_comm = nullptr;
+  void** dev[] = {(void**)&s->d_agc_x_am, (void**)&s->d_agc_x_lin, (void**)&s->d_agc_y_lin, (void**)&s->d_agc_pow, &s->d_ring,
+                  (void**)&s->d_spec, (void**)&s->d_tmp0, (void**)&s->d_tmp1, (void**)&s->d_energy, (void**)&s->d_tw2048,
+                  (void**)&s->d_params, (void**)&s->d_state, (void**)&s->d_resp, (void**)&s->d_audio_resp,
+                  (void**)&s->d_audio_hist, (void**)&s->d_pcm, (void**)&s->d_status, (void**)&s->d_filt,
+                  (void**)&s->d_windows, (void**)&s->d_work_fm, (void**)&s->d_work_am, (void**)&s->d_work_lin};
+  for (void** p : dev) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  void** host[] = {&s->h_iq, (void**)&s->h_pcm, (void**)&s->h_status};
+  for (void** p : host) {
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+  }
+  cudaStream_t* sts[] = {&s->s_in, &s->s_comp, &s->s_out, &s->s_fm, &s->s_am, &s->s_lin, &s->s_fft};
+  for (auto st : sts) {
+    if (*st) cudaStreamDestroy(*st);
+    *st = nullptr;
+  }
+  cudaEvent_t* evs[] = {&s->e_pushed, &s->e_fft0, &s->e_fft1, &s->e_chan1, &s->e_fork, &s->e_am, &s->e_lin, &s->e_fm,
+                        &s->e_comp_done[0], &s->e_comp_done[1], &s->e_fetched[0], &s->e_fetched[1], &s->e_spec_ready[0],
+                        &s->e_spec_ready[1], &s->e_spec_free[0], &s->e_spec_free[1], &s->e_t0, &s->e_t1};
+  for (auto e : evs) {
+    if (*e) cudaEventDestroy(*e);
+    *e = nullptr;
+  }
+  for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
+  s->ev_pool.clear();
+  s->ev_used.clear();
+  s->ev_next = 0;
+  s->committed = false;
+}
+
+int ka9q_stream_destroy(ka9q_stream* s) {
+  if (!s) return 0;
+  release_resources(s);
   bigfft_plan_destroy(&s->fwd);
   bigfft_plan_destroy(&s->p2048);
-  void* dev[] = {s->d_agc_x_am, s->d_agc_x_lin, s->d_agc_y_lin, s->d_agc_pow, s->d_ring, s->d_spec, s->d_tmp0, s->d_tmp1, s->d_energy, s->d_tw2048, s->d_params, s->d_state, s->d_resp,
-                 s->d_audio_resp, s->d_audio_hist, s->d_pcm, s->d_status, s->d_filt, s->d_windows, s->d_work_fm,
-                 s->d_work_am, s->d_work_lin};
-  for (void* p : dev)
-    if (p) cudaFree(p);
-  if (s->h_iq) cudaFreeHost(s->h_iq);
-  if (s->h_pcm) cudaFreeHost(s->h_pcm);
-  if (s->h_status) cudaFreeHost(s->h_status);
-  cudaStream_t sts[] = {s->s_in, s->s_comp, s->s_out, s->s_fm, s->s_am, s->s_lin};
-  for (auto st : sts)
-    if (st) cudaStreamDestroy(st);
-  cudaEvent_t evs[] = {s->e_pushed, s->e_fft0, s->e_fft1, s->e_chan1, s->e_fork, s->e_am, s->e_lin, s->e_fm,
-                       s->e_comp_done[0], s->e_comp_done[1], s->e_fetched[0], s->e_fetched[1]};
-  for (auto e : evs)
-    if (e) cudaEventDestroy(e);
   delete s;
   return 0;
 }
-
-
 
 // Overlap of the forward FFT (batch k+1) with the channel kernels (batch k) is on by default; switching it off
 // serialises them so that per-kernel event timings are those of each kernel running alone.
@@ -924,17 +974,6 @@ void ka9q_host_free(void* p) {
 // ------------------------------------------------------------------ NCCL spectrum broadcast (libnccl dlopen'ed)
 // The only inter-GPU exchange of the path: the rank that ingested the block broadcasts N*8 bytes of
 // spectrum per block; channels never move.
-
-typedef struct ncclComm* k9_ncclComm_t;
-typedef struct {
-  char internal[128];
-} k9_ncclUniqueId;
-static int (*p_ncclGetUniqueId)(k9_ncclUniqueId*);
-static int (*p_ncclCommInitRank)(k9_ncclComm_t*, int, k9_ncclUniqueId, int);
-static int (*p_ncclBroadcast)(const void*, void*, size_t, int, int, k9_ncclComm_t, cudaStream_t);
-static int (*p_ncclCommDestroy)(k9_ncclComm_t);
-static int (*p_ncclAllGather)(const void*, void*, size_t, int, k9_ncclComm_t, cudaStream_t);
-static const char* (*p_ncclGetErrorString)(int);
 
 static int load_nccl() {
   static int state = 0;  // 0 untried, 1 ok, -1 failed

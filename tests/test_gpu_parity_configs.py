@@ -1,0 +1,213 @@
+"""GPU parity at the BASELINE.json geometries (run with -m gpu on the B200 box): the configs the metric is quoted on, at
+their own FFT sizes and depths, against the VERBATIM reference (oracle/_ref) on identical int16 I/Q.
+
+  cfg2  one USB channel at 1.92 MS/s (N = 81 920), 150 blocks, AGC-gain trajectory           SURVEY 8d-2
+  cfg4  1024 mixed FM/FM/AM/USB channels at 19.2 MS/s (N = 819 200 = 80*80*128), every 16th   SURVEY 8d-4
+        channel (all four modes, incl. channel 0 at -Fs/2 whose window wraps) vs the reference
+  cfg5  8192 NBFM channels at 61.44 MS/s (N = 2 621 440) on bench.py's own comb stimulus,     SURVEY 8d-5
+        32 sampled channels x 25 blocks vs the reference
+  FM squelch: every block of the carrier-drop test is compared, with the bound stated in the test
+
+Tolerances are north_star's: filter output <= 1e-5 relative RMS, PCM within +-1 LSB."""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from ka9q_sdr_b200 import channelizer as ch, modes, synth, workloads
+
+pytestmark = pytest.mark.gpu
+
+FILT_TOL = 1e-5
+PCM_TOL = 1
+
+
+def rel_rms(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(b))
+
+
+def pcm_channels(mode):
+    m = modes.get_mode(mode)
+    return m.channels if m.demod_type == modes.LINEAR_DEMOD else 1
+
+
+def check_pcm(mode, got, want, olen, label=""):
+    n = min(got.size, want.size)
+    d = np.abs(got[:n].astype(np.int32) - want[:n].astype(np.int32))
+    skip = 0 if modes.get_mode(mode).demod_type == modes.FM_DEMOD else olen * pcm_channels(mode)
+    assert d[skip:].max() <= PCM_TOL, f"{label}{mode}: PCM differs by {d[skip:].max()} LSB"
+    assert (d[skip:] == 0).mean() > 0.97, f"{label}{mode}: only {(d[skip:] == 0).mean():.4f} of samples bit-equal"
+
+
+def run_all(c, iq, L, want_status=True):
+    return c.run(iq, want_status=want_status)
+
+
+@pytest.fixture()
+def mkl_ref(ref):
+    """The big-N configs run the reference with MKL's fp32 FFT behind the FFTW shim (the double-precision stand-in FFT
+    takes minutes at N = 2.6 M); falls back to the stand-in where MKL is not loadable."""
+    ok = ref.set_fft_backend("mkl")
+    yield ref
+    ref.set_fft_backend("standin")
+    del ok
+
+
+def test_cfg2_usb_at_its_own_rate_150_blocks(ref):
+    """cfg2 as BASELINE.json states it: 1.92 MS/s (D = 40, N = 81 920 = 256*320), one USB channel, 150 blocks = 3 s with
+    the slow 6 dB ramp, so AGC attack, hang and recovery all occur (linear.c:251-299)."""
+    nb = 150
+    cfg = synth.cfg2_usb(nb)            # samprate 1 920 000
+    fs, L, M, D, N = cfg["samprate"], cfg["L"], cfg["M"], cfg["D"], cfg["N"]
+    assert (fs, N) == (1920000, 81920)
+    k = cfg["bins"][0]
+    c = ch.Channelizer(fs, L, M, D, max_blocks=6, capture_filter_output=False)
+    c.add_channel("USB", k)
+    c.commit()
+    pcm, st = c.run(cfg["iq"])
+    r = ref.chain_run("USB", fs, L, M, D, cfg["iq"], carrier_hz=k * fs / N, lo_cycles=-k / N, pkt_samples=4096)
+    check_pcm("USB", c.channel_pcm(pcm, 0), r.pcm, L // D)
+    np.testing.assert_allclose(st["agc_gain"][5:, 0], r.status["agc_gain"][5:nb], rtol=2e-4)
+    g = st["agc_gain"][5:, 0]
+    assert g.max() / g.min() > 1.5       # the AGC really moved (ramp of 6 dB)
+    c.close()
+
+
+def _cfg4_stimulus(plan, nb, tested):
+    """All 1024 channels are demodulated; carriers are put on the tested channels and on each one's upper neighbour
+    (time-domain synthesis on the exact bin grid costs O(carriers x samples)); AWGN fills the band."""
+    fs, N, L = plan.samprate, plan.N, plan.L
+    n = nb * L
+    rng = np.random.default_rng(plan.seed)
+    x = synth.awgn(rng, n, plan.sigma)
+    amp = plan.amplitude          # 0.005: 128 carriers peak at 0.64, no int16 clipping; ~36 dB in-channel SNR
+    for j in sorted(set(tested) | {j + 1 for j in tested if j + 1 < len(plan.channels)}):
+        s = plan.channels[j]
+        f_c = s.bin * fs / N
+        tone = 300.0 + 37.0 * (j % 64)
+        if s.mode == "FM":
+            x += synth.fm_carrier(n, fs, f_c, tone, 2500.0, amp, phase0=0.37 * j)
+        elif s.mode == "AM":
+            x += synth.am_carrier(n, fs, f_c, 1000.0, 0.5, amp)
+        else:
+            x += synth.ssb_two_tone(n, fs, f_c, (tone, tone + 600.0), (amp / 2, amp / 2))
+    return synth._quantize(x)
+
+
+def test_cfg4_1024_mixed_channels_at_N_819200(mkl_ref):
+    """cfg4 at its geometry: N = 819 200 (three generic FFT passes 80*80*128), 1024 channels in the repeating pattern
+    FM, FM, AM, USB on the 18.75 kHz raster k_j = 800 (j - 512); every 16th channel (stepping through all four modes)
+    against the reference, incl. channel 0 at -Fs/2 whose 2048-bin window wraps around the spectrum."""
+    ref = mkl_ref
+    plan = workloads.cfg4()
+    assert plan.N == 819200 and len(plan.channels) == 1024
+    nb = 5
+    tested = [16 * i + (i % 4) for i in range(64)]
+    assert tested[0] == 0 and {plan.channels[j].mode for j in tested} == {"FM", "AM", "USB"}
+    iq = _cfg4_stimulus(plan, nb, tested)
+    fs, L, M, D, N = plan.samprate, plan.L, plan.M, plan.D, plan.N
+    c = ch.Channelizer(fs, L, M, D, max_blocks=nb, capture_filter_output=True)
+    for s in plan.channels:
+        c.add_channel(s.mode, s.bin)
+    c.commit()
+    pcm, st = c.process(iq)
+    filt = {j: c.filter_output(j, nb) for j in tested}
+
+    def one(j):
+        s = plan.channels[j]
+        return j, ref.chain_run(s.mode, fs, L, M, D, iq, carrier_hz=s.bin * fs / N, lo_cycles=-s.bin / N,
+                                want_filt=s.mode != "USB", pkt_samples=4096)
+
+    with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(one, tested))
+    worst = 0.0
+    for j, r in results:
+        s = plan.channels[j]
+        if r.filt is not None:
+            e = rel_rms(filt[j], r.filt[:nb])
+            worst = max(worst, e)
+            assert e < FILT_TOL, f"channel {j} ({s.mode} @ bin {s.bin}): filter output rel-RMS {e:.2e}"
+        check_pcm(s.mode, c.channel_pcm(pcm, j), r.pcm, L // D, label=f"ch{j} ")
+    # FM channels with a carrier open their squelch, the AGC of the AM / USB ones settled
+    for j in tested:
+        if plan.channels[j].mode == "FM":
+            assert st["squelch_open"][1:, j].all(), j
+    print(f"cfg4: worst filter-output rel-RMS over {len(tested)} channels = {worst:.2e}")
+    c.close()
+
+
+def test_cfg5_bench_stimulus_32_channels_25_blocks(mkl_ref):
+    """cfg5 at survey depth on the stimulus bench.py itself runs (synth.comb_spectrum_iq: 8192 phase-continuous NBFM
+    carriers, AWGN): the full 8192-channel plan on the GPU, 32 sampled channels x 25 blocks against the reference."""
+    ref = mkl_ref
+    plan = workloads.cfg5()
+    nb = 25
+    fs, L, M, D, N = plan.samprate, plan.L, plan.M, plan.D, plan.N
+    iq = synth.comb_spectrum_iq(fs, nb, [s.bin for s in plan.channels], plan.seed, plan.amplitude, plan.sigma,
+                                deviation=plan.deviation)["iq"]
+    B = 5
+    c = ch.Channelizer(fs, L, M, D, max_blocks=B, capture_filter_output=False)
+    for s in plan.channels:
+        c.add_channel(s.mode, s.bin, low=s.low, high=s.high)
+    c.commit()
+    pcm, st = c.run(iq)
+    tested = [256 * i + 7 * (i % 5) for i in range(32)]      # spread over the band, odd and even pair slots
+    tested[0], tested[-1] = 0, 8191                            # both band edges
+
+    def one(j):
+        s = plan.channels[j]
+        return j, ref.chain_run("FM", fs, L, M, D, iq, carrier_hz=s.bin * fs / N, lo_cycles=-s.bin / N, low=s.low,
+                                high=s.high, pkt_samples=4096)
+
+    with ThreadPoolExecutor(min(32, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(one, tested))
+    exact = []
+    for j, r in results:
+        got = c.channel_pcm(pcm, j)
+        check_pcm("FM", got, r.pcm, L // D, label=f"ch{j} ")
+        n = min(got.size, r.pcm.size)
+        exact.append(float((got[:n] == r.pcm[:n]).mean()))
+        np.testing.assert_allclose(st["bb_power"][:, j], r.status["bb_power"][:nb], rtol=2e-4)
+    assert st["squelch_open"][1:].mean() > 0.999
+    print(f"cfg5: PCM bit-equal fraction over 32 channels x 25 blocks: min {min(exact):.4f} mean {np.mean(exact):.4f}")
+    c.close()
+
+
+def test_fm_squelch_every_block_compared(ref):
+    """Carrier drops out for blocks 4..9 (noise only) and returns at block 10. Every block is compared with the reference:
+
+    * blocks with a carrier, and blocks with the squelch shut (zeros, fm.c:155-160): +-1 LSB;
+    * the block where the squelch re-opens on a zeroed discriminator state (fm.c:156: cargf(samp * 0)): +-1 LSB as well —
+      the kernel hands atan2 the same zero signs as the reference;
+    * block 4 (noise demodulated through the threshold-extension blanker, fm.c:121-142, squelch still open) and the
+      blocks its de-emphasis-filter tail reaches (5, 6): the blanking decision |y|^2 > 0.3025 avg^2 rides on a block
+      average that the kernel reduces as a tree and gcc sums in vector lanes, so a sample sitting within an ulp of the
+      threshold can flip, and one flip replaces a run of samples. Bound asserted: >= 98 % of those blocks' samples within
+      +-1 LSB (measured figures are printed and recorded in DESIGN.md)."""
+    cfg = synth.cfg1_fm(12)
+    rng = np.random.default_rng(9)
+    iq = cfg["iq"].copy()
+    L = cfg["L"]
+    iq[2 * 4 * L:2 * 10 * L] = synth._quantize(synth.awgn(rng, 6 * L, 0.02))
+    fs, M, D, N = cfg["samprate"], cfg["M"], cfg["D"], cfg["N"]
+    k = cfg["bins"][0]
+    c = ch.Channelizer(fs, L, M, D, max_blocks=4)
+    c.add_channel("FM", k)
+    c.commit()
+    pcm, st = c.run(iq)
+    r = ref.chain_run("FM", fs, L, M, D, iq, carrier_hz=k * fs / N, lo_cycles=-k / N)
+    got = c.channel_pcm(pcm, 0).reshape(12, -1)
+    want = r.pcm.reshape(12, -1)
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert (st["squelch_open"][6:9, 0] == 0).all() and st["squelch_open"][11, 0] == 1
+    report = {b: (int(d[b].max()), float((d[b] > 1).mean())) for b in range(12)}
+    print("squelch test, per block (max |diff| LSB, fraction > 1 LSB):", report)
+    noise_blocks = (4, 5, 6)
+    for b in range(12):
+        if b in noise_blocks:
+            assert (d[b] <= PCM_TOL).mean() >= 0.98, f"block {b}: {report[b]}"
+        else:
+            assert d[b].max() <= PCM_TOL, f"block {b}: {report[b]}"
+    assert np.abs(got[8]).max() == 0      # shut squelch sends zeros (fm.c:155-160)
+    c.close()
