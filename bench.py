@@ -8,8 +8,11 @@ plus the roofline of the dominant kernel and the reference's CPU path timed on t
 One "step" = one pass of the hot path over one batch of B consecutive 20 ms blocks of synthetic I/Q
 (forward FFT once per block + every channel: bin rotation, response multiply, inverse FFT, overlap discard, FM
 demodulation, de-emphasis filter, int16 PCM).
-Multi-GPU (torchrun, one rank per GPU): weak scaling — every rank runs the full channel plan; rank 0 ingests the
-stream, runs the forward FFT and broadcasts the spectrum with NCCL (the only exchange of the path).
+Multi-GPU (torchrun, one rank per GPU), default `--mgpu sharded`: STRONG scaling of the same workload — cfg5's 8192
+channels are sharded frequency-contiguously over the ranks, the forward FFT is sharded by block, and every producer stores
+each peer's arc of the spectrum into that peer's HBM over NVLink (csrc/mgpu.cu; `--transport nccl` uses grouped
+ncclSend/ncclRecv instead). A WEAK line (every rank its own 8192 distinct channels, no inter-rank coupling at all) is
+measured in the same run and reported under "weak".
 """
 from __future__ import annotations
 
@@ -263,26 +266,35 @@ def run_ours(args, plan):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B = args.blocks
-    if multi and args.mgpu == "allgather":
+    sharded = multi and args.mgpu == "sharded"
+    if multi and args.mgpu in ("allgather", "sharded"):
         B = max(B, world)
         B += (-B) % world          # the block-sharded forward FFT needs blocks_per_step % n_gpus == 0
+    from ka9q_sdr_b200 import workloads
+    my_channels = workloads.shard_contiguous(plan, rank, world) if sharded else plan.channels
     c = ch.Channelizer(plan.samprate, plan.L, plan.M, plan.D, device=local, max_blocks=B)
-    for spec in plan.channels:
+    for spec in my_channels:
         c.add_channel(spec.mode, spec.bin, low=spec.low, high=spec.high)
     c.commit()
     K = c.nchan
+    K_total = len(plan.channels) if sharded else world * K     # channels demodulated by the whole job
 
     # synthetic input (rank 0 ingests the stream); pinned host buffers for the end-to-end leg
     nbytes_in = B * plan.L * 4
     pin_in = ch.PinnedBuffer(nbytes_in, np.int16)
-    if rank == 0 or args.mgpu in ("allgather", "replicate"):
-        pin_in.array[:] = make_input(plan, B)   # block-sharded FFT: every rank ingests the (int16) stream
+    if rank == 0 or args.mgpu in ("allgather", "replicate", "sharded"):
+        pin_in.array[:] = make_input(plan, B)   # block-sharded FFT: every rank ingests (its part of) the int16 stream
     pin_pcm = [ch.PinnedBuffer(B * c.pcm_stride * 2, np.int16) for _ in range(2)]
     in_ptr = C.c_void_p(pin_in.ptr)
     pcm_ptrs = [C.c_void_p(p.ptr) for p in pin_pcm]
 
     replicate = multi and args.mgpu == "replicate"
-    if multi and not replicate:
+    arc = None
+    if sharded:
+        from ka9q_sdr_b200 import mgpu
+        mgpu.setup_sharded(c, rank, world, ch.MGPU_NCCL if args.transport == "nccl" else ch.MGPU_P2P)
+        arc = c.needed_bins()
+    if multi and not replicate and not sharded:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(ch.nccl_unique_id()), dtype=torch.uint8))
@@ -311,11 +323,15 @@ def run_ours(args, plan):
     def step_resident():
         if not multi or replicate:
             c.compute_resident(B)
+        elif sharded:
+            c.mgpu_compute(B, resident=True)
         else:
             spectrum_step()
             c.compute_channels_only(B)
 
     e2e_count = [0]
+    e2e_block0 = [0]      # stream position (in blocks) where the end-to-end leg starts
+    e2e_h2d = [nbytes_in]
 
     def step_e2e():
         """One batch through the public streaming calls: H2D of the batch's I/Q from pinned host memory, forward FFT +
@@ -325,11 +341,20 @@ def run_ours(args, plan):
         leg — never idles on a host round trip."""
         i = e2e_count[0]
         e2e_count[0] += 1
-        if not multi or rank == 0 or args.mgpu in ("allgather", "replicate"):
+        if sharded:
+            # every rank uploads only the samples its own blocks of the batch need (its blocks + M-1 samples of overlap)
+            fb = e2e_block0[0] + i * B
+            if i == 0:
+                e2e_h2d[0] = mgpu.push_batch_share(c, pin_in.ptr, 4, fb, B, B * plan.L)
+            mgpu.push_batch_share(c, pin_in.ptr, 4, fb + B, B, B * plan.L)
+            c.mgpu_compute(B, resident=False)
+        elif not multi or rank == 0 or args.mgpu in ("allgather", "replicate"):
             if i == 0:
                 c.push(in_ptr, B)      # prime: batch 0
             c.push(in_ptr, B)          # batch i+1 goes up while batch i is computed (the ring holds two batches)
-        if not multi or replicate:
+        if sharded:
+            pass
+        elif not multi or replicate:
             c.compute(B)
         else:
             # every rank returns its own PCM rows to the host
@@ -390,9 +415,29 @@ def run_ours(args, plan):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total_max = float(t.item())
     ms_per_step = ms_total_max / args.steps
-    ms_blocks_per_s = world * K * (B * plan.L / 1e6) / (ms_per_step / 1e3)   # channel·MS/s over all ranks
+    ms_blocks_per_s = K_total * (B * plan.L / 1e6) / (ms_per_step / 1e3)   # channel·MS/s of the whole job
+
+    # ---- 1 block per step: the latency-oriented operating point (a 20 ms block as the reference processes it); the
+    # responses are then fetched from DRAM every block instead of being re-read from L2 for blocks 2..B of a batch
+    b1 = None
+    if not multi:
+        for _ in range(5):
+            c.compute_resident(1)
+        barrier()
+        c.timer_start()
+        n1 = max(20, args.steps)
+        for _ in range(n1):
+            c.compute_resident(1)
+        ms1, cl1 = c.timer_stop()
+        barrier()
+        b1 = {"blocks_per_step": 1, "ms_per_step": ms1 / n1, "value": K * (plan.L / 1e6) / (ms1 / n1 / 1e3), "unit": UNIT,
+              "speedup_over_realtime": 20.0 / (ms1 / n1)}
 
     # ---- end-to-end leg (host pinned buffers, H2D + D2H inside the timed region)
+    c.sync()
+    if sharded:
+        # streaming continues where the resident leg left the stream: the next batch boundary
+        e2e_block0[0] = c.blocks_done()
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     barrier()
@@ -406,9 +451,49 @@ def run_ours(args, plan):
     if multi:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    e2e_value = world * K * (B * plan.L / 1e6) / e2e_s
-    h2d = nbytes_in * (world if (multi and args.mgpu in ("allgather", "replicate")) else 1)
-    d2h = world * B * c.pcm_stride * 2
+    e2e_value = K_total * (B * plan.L / 1e6) / e2e_s
+    launches_pc, pcm_stride = c.launches_per_call, c.pcm_stride
+    if sharded:
+        t = torch.tensor([float(e2e_h2d[0]), float(B * c.pcm_stride * 2)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)                      # bytes over all ranks
+        h2d, d2h = int(t[0].item()), int(t[1].item())
+    else:
+        h2d = nbytes_in * (world if (multi and args.mgpu in ("allgather", "replicate")) else 1)
+        d2h = world * B * c.pcm_stride * 2
+
+    # ---- weak line (multi-GPU): every rank demodulates its own 8192 DISTINCT channels (carrier raster shifted by 16 bins
+    # per rank) from the stream; every rank ingests the stream and runs its own forward FFT, so the ranks are not coupled
+    # at all (the I/Q stream is a multicast any number of receivers can join). Device-resident, same timing rules.
+    weak = None
+    if multi and args.weak:
+        c.close()
+        wplan = make_plan(args.config, args.channels) if args.config != "cfg5" else workloads.cfg5(args.channels or 8192, 16 * rank)
+        Bw = args.blocks
+        cw = ch.Channelizer(wplan.samprate, wplan.L, wplan.M, wplan.D, device=local, max_blocks=Bw)
+        for spec in wplan.channels:
+            cw.add_channel(spec.mode, spec.bin, low=spec.low, high=spec.high)
+        cw.commit()
+        for _ in range(2):
+            cw.push(in_ptr, Bw)
+            cw.compute(Bw)
+            cw.sync()
+        for _ in range(200):
+            cw.compute_resident(Bw)
+        cw.sync()
+        if multi:
+            dist.barrier()
+        cw.timer_start()
+        for _ in range(args.steps):
+            cw.compute_resident(Bw)
+        msw, _ = cw.timer_stop()
+        t = torch.tensor([msw], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        msw = float(t.item()) / args.steps
+        weak = {"scaling": "weak", "channels_per_gpu": cw.nchan, "channels_total": world * cw.nchan, "blocks_per_step": Bw,
+                "ms_per_step": msw, "value": world * cw.nchan * (Bw * wplan.L / 1e6) / (msw / 1e3), "unit": UNIT,
+                "coupling": "none: every rank ingests the stream and runs its own forward FFT on distinct carriers "
+                            "(raster shifted by 16 bins per rank)"}
+        cw.close()
 
     if rank != 0:
         if multi:
@@ -417,32 +502,38 @@ def run_ours(args, plan):
         return
 
     # ---- roofline of the dominant kernel (the FM channel kernel), measured live with CUDA events
-    chan_bytes, stream_bytes = algorithmic_bytes(plan, B)
+    import copy
+    rplan = copy.copy(plan)
+    rplan.channels = my_channels                 # the dominant kernel's launch covers this rank's channels
+    chan_bytes, stream_bytes = algorithmic_bytes(rplan, B)
     peak, peak_src = measured_peak_hbm()
     dom = max(("fm", "am", "linear"), key=lambda k: classes[k][0])
     dom_ms, dom_n = classes[dom]
     roofline = None
     if dom_n:
         avg_ms = dom_ms / dom_n
-        ach = chan_bytes / (avg_ms / 1e3) / 1e9 if len({m.mode for m in plan.channels}) == 1 else None
+        ach = chan_bytes / (avg_ms / 1e3) / 1e9 if len({m.mode for m in rplan.channels}) == 1 else None
         if ach is None:
             # mixed plans: only the dominant class's channels count for its kernel
-            from ka9q_sdr_b200 import modes, workloads
+            from ka9q_sdr_b200 import modes
             olen = plan.L // plan.D
             dt = {"fm": 2, "am": 1, "linear": 0}[dom]
             cb = sum(workloads.channel_block_bytes(dt, modes.get_mode(s.mode).channels if dt == 0 else 1, olen,
                                                    modes.get_mode(s.mode).flat)
-                     for s in plan.channels if modes.get_mode(s.mode).demod_type == dt) * B
+                     for s in rplan.channels if modes.get_mode(s.mode).demod_type == dt) * B
             ach = cb / (avg_ms / 1e3) / 1e9
-        traffic = None
+        # DRAM traffic per launch comes from an `ncu --set full` capture of this same workload (profiles/traffic.json
+        # names the report); it only applies to the single-GPU launch shape it was captured on
+        traffic = traffic_src = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and not multi and B == 4 and args.config == "cfg5" and not args.channels:
             try:
-                traffic = json.load(open(tp)).get(f"{dom}_kernel_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic, traffic_src = tj.get(f"{dom}_kernel_bytes_per_launch"), tj.get("source")
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "launches": dom_n,
                     "algorithmic_bytes_per_launch": chan_bytes,
                     "share_of_step": dom_ms / ms_serial if ms_serial else None,
@@ -464,15 +555,23 @@ def run_ours(args, plan):
         except Exception as e:
             cpu_chan = {"error": str(e)}
 
-    launches_per_step = c.launches_per_call + (1 if multi else 0)
-    work_mb = (K * 2048 * 8 + K * 2048 * 4 + B * plan.N * 8 * 2 + B * c.pcm_stride * 2) / 1e6
+    launches_per_step = launches_pc + ((4 if args.transport == "p2p" else 1) if sharded else (1 if multi and not replicate else 0))
+    work_mb = (K * 2048 * 8 + K * 2048 * 4 + B * plan.N * 8 * 2 + B * pcm_stride * 2) / 1e6
     line = {
         "metric": METRIC, "value": ms_blocks_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if sharded else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": plan.name, "channels_per_gpu": K, "samprate": plan.samprate, "L": plan.L, "M": plan.M,
+        "config": {"workload": plan.name, "channels_per_gpu": K, "channels_total": K_total, "samprate": plan.samprate,
+                   "L": plan.L, "M": plan.M,
                    "N": plan.N, "decimate": plan.D, "blocks_per_step": B, "block_ms": 20,
                    "parallelism": "1 GPU" if not multi else {
+                       "sharded": f"{K_total} channels sharded frequency-contiguously over {world} GPUs (strong scaling); "
+                                  f"forward FFT sharded by block ({B // world} of {B} blocks per rank and step); every "
+                                  "producer sends each peer only the arc of the spectrum its channels read: "
+                                  + ("peer-memory stores over NVLink from a copy kernel of this library + device-memory "
+                                     "sequence flags (no collective library on the data path)" if args.transport == "p2p"
+                                     else "grouped ncclSend/ncclRecv"),
                        "replicate": f"channels x{world} (weak); every rank ingests the int16 stream and runs its own "
                                     "forward FFT, no data-path collective",
                        "allgather": f"channels x{world} (weak); forward FFT sharded by block + NCCL all-gather of spectra",
@@ -491,6 +590,15 @@ def run_ours(args, plan):
         "class_ms_per_step": {k: v[0] / nser for k, v in classes.items()},
         "serialised_ms_per_step": ms_serial / nser,
     }
+    if b1:
+        line["operating_points"] = [b1]
+    if weak:
+        line["weak"] = weak
+    if sharded:
+        arc_lo, arc_len = arc
+        line["exchange"] = {"transport": args.transport, "arc_bins_this_rank": arc_len,
+                            "nvlink_bytes_in_per_step_this_rank": int(arc_len * 8 * B * (world - 1) / world),
+                            "broadcast_would_move_bytes_per_step": int(plan.N * 8 * B * (world - 1) / world)}
     print(json.dumps(line))
     if multi:
         dist.barrier()
@@ -510,10 +618,13 @@ def main():
                     help="timed steps of the end-to-end leg (the last batch's copy-out drains inside the timed region)")
     ap.add_argument("--ref-blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mgpu", default="replicate", choices=["replicate", "allgather", "broadcast"],
-                    help="multi-GPU spectrum distribution: replicate = every rank ingests the stream and runs its own "
-                         "forward FFT (no collective); allgather = FFT sharded by block + NCCL all-gather; broadcast = "
-                         "rank 0 transforms, NCCL broadcast")
+    ap.add_argument("--mgpu", default="sharded", choices=["sharded", "replicate", "allgather", "broadcast"],
+                    help="multi-GPU form: sharded (default) = channels sharded over the ranks, FFT sharded by block, "
+                         "per-peer spectrum arcs over NVLink (strong scaling); replicate = every rank runs the full "
+                         "plan on its own FFT (weak, no coupling); allgather / broadcast = full-plan ranks with the "
+                         "spectrum all-gathered / broadcast by NCCL")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="sharded mode: exchange transport")
+    ap.add_argument("--no-weak", dest="weak", action="store_false", help="skip the weak-scaling line of multi-GPU runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     plan = make_plan(args.config, args.channels)

@@ -219,6 +219,8 @@ int ka9q_stream_num_channels(const ka9q_stream *s);
 long long ka9q_stream_pcm_stride(const ka9q_stream *s);
 int ka9q_stream_pcm_offset(const ka9q_stream *s, int chan);
 int ka9q_stream_olen(const ka9q_stream *s);
+/* blocks of the stream consumed so far (the next streaming compute starts at this block) */
+long long ka9q_stream_blocks_done(const ka9q_stream *s);
 int ka9q_stream_fft_size(const ka9q_stream *s);
 int ka9q_stream_launches_per_call(const ka9q_stream *s);
 
@@ -271,6 +273,29 @@ int ka9q_stream_nccl_init(ka9q_stream *s, const void *id128, int rank, int nrank
 int ka9q_stream_nccl_broadcast_spectrum(ka9q_stream *s, int nblocks, int root);
 /* every rank transformed its nblocks/nranks blocks (compute_fft_blocks); gather all nblocks spectra on every rank */
 int ka9q_stream_nccl_allgather_spectrum(ka9q_stream *s, int nblocks);
+
+/* Channel-sharded multi-GPU: one process per GPU, each holding a frequency-contiguous share of the channels.
+ * Per batch the forward FFT is sharded by block (rank q transforms blocks [q*nb/G, (q+1)*nb/G)), every producer sends each
+ * peer only the arc of the spectrum that peer's channels read, then every rank runs its own channel kernels. Transports:
+ * P2P = a copy kernel of this library stores into the peers' spectrum buffers over NVLink (peer memory mapped with CUDA
+ * IPC) and hands over with sequence flags in device memory; NCCL = grouped ncclSend / ncclRecv (cross-check).
+ * The host plumbing (torch.distributed, MPI, a pipe ...) only all-gathers three small blobs at set-up time:
+ *   ka9q_stream_needed_bins -> (lo, len) of this rank's arc;  ka9q_stream_mgpu_export -> 128-byte IPC handle blob. */
+#define KA9Q_MGPU_NCCL 1
+#define KA9Q_MGPU_P2P 2
+int ka9q_stream_needed_bins(ka9q_stream *s, long long *lo, long long *len);
+int ka9q_stream_mgpu_export(ka9q_stream *s, void *blob128);
+int ka9q_stream_mgpu_setup(ka9q_stream *s, int transport, int rank, int nranks, const long long *lo_all,
+                           const long long *len_all, const void *blobs /* nranks x 128 bytes, P2P only */);
+/* sample range (absolute stream positions) this rank must hold to transform its blocks of the batch at first_block */
+int ka9q_stream_mgpu_input_range(ka9q_stream *s, long long first_block, int nblocks, long long *first_sample,
+                                 long long *nsamples);
+/* H2D copy of stream samples [first_sample, first_sample + nsamples) to their place in the device ring */
+int ka9q_stream_push_at(ka9q_stream *s, const void *iq, long long first_sample, long long nsamples);
+/* one batch: FFT of this rank's blocks, exchange, channel kernels. resident != 0 re-runs the last pushed batch. */
+int ka9q_stream_mgpu_compute(ka9q_stream *s, int nblocks, int resident);
+/* nonzero if a wait on a peer timed out (P2P transport; valid after ka9q_stream_sync) */
+int ka9q_stream_mgpu_error(ka9q_stream *s);
 
 /* Introspection for parity tests (device -> host copies, synchronous). */
 int ka9q_stream_get_response(ka9q_stream *s, int chan, KA9Q_CFLOAT *out2048, float *noise_gain);

@@ -64,6 +64,8 @@ EXPORTED = [
     "ka9q_stream_timer_stop", "ka9q_osc_run", "ka9q_stream_wait_fetch", "ka9q_stream_compute_fft_blocks",
     "ka9q_stream_nccl_allgather_spectrum", "ka9q_stream_set_overlap", "ka9q_ingest_init", "ka9q_ingest_datagram",
     "ka9q_rtp_process", "ka9q_pcm_packetise", "ka9q_stream_wait_fetched", "ka9q_status_encode_signals",
+    "ka9q_stream_needed_bins", "ka9q_stream_mgpu_export", "ka9q_stream_mgpu_setup", "ka9q_stream_mgpu_input_range",
+    "ka9q_stream_push_at", "ka9q_stream_mgpu_compute", "ka9q_stream_mgpu_error", "ka9q_stream_blocks_done",
 ]
 
 
@@ -119,6 +121,15 @@ def lib():
     L.ka9q_stream_timer_start.argtypes = [vp]
     L.ka9q_stream_timer_stop.argtypes = [vp, C.POINTER(cf), C.POINTER(cf), C.POINTER(ci)]
     L.ka9q_osc_run.argtypes = [C.c_double, C.c_double, C.c_long, vp]
+    L.ka9q_stream_needed_bins.argtypes = [vp, C.POINTER(cll), C.POINTER(cll)]
+    L.ka9q_stream_mgpu_export.argtypes = [vp, vp]
+    L.ka9q_stream_mgpu_setup.argtypes = [vp, ci, ci, ci, C.POINTER(cll), C.POINTER(cll), vp]
+    L.ka9q_stream_mgpu_input_range.argtypes = [vp, cll, ci, C.POINTER(cll), C.POINTER(cll)]
+    L.ka9q_stream_push_at.argtypes = [vp, vp, cll, cll]
+    L.ka9q_stream_mgpu_compute.argtypes = [vp, ci, ci]
+    L.ka9q_stream_mgpu_error.argtypes = [vp]
+    L.ka9q_stream_blocks_done.argtypes = [vp]
+    L.ka9q_stream_blocks_done.restype = cll
     L.ka9q_host_alloc.argtypes = [C.c_size_t]
     L.ka9q_host_alloc.restype = vp
     L.ka9q_host_free.argtypes = [vp]

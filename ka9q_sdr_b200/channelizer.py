@@ -14,6 +14,7 @@ from . import _lib
 from .modes import FM_DEMOD, LINEAR_DEMOD, Mode, get_mode
 
 IQ_S16, IQ_S8 = 1, 2
+MGPU_NCCL, MGPU_P2P = 1, 2
 FLAG_ISB, FLAG_FLAT, FLAG_PLL, FLAG_SQUARE = 1, 2, 4, 8
 
 
@@ -197,6 +198,43 @@ class Channelizer:
 
     def nccl_broadcast_spectrum(self, nblocks: int, root: int = 0):
         _lib.check(self.lib.ka9q_stream_nccl_broadcast_spectrum(self.h, nblocks, root), "nccl_broadcast_spectrum")
+
+    # -- channel-sharded multi-GPU (include/ka9q_b200.h: ka9q_stream_mgpu_*) ---------------------------------------
+    def needed_bins(self):
+        lo, ln = C.c_longlong(), C.c_longlong()
+        _lib.check(self.lib.ka9q_stream_needed_bins(self.h, C.byref(lo), C.byref(ln)), "needed_bins")
+        return lo.value, ln.value
+
+    def mgpu_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.check(self.lib.ka9q_stream_mgpu_export(self.h, buf), "mgpu_export")
+        return buf.raw
+
+    def mgpu_setup(self, transport: int, rank: int, nranks: int, arcs, blobs: bytes | None = None):
+        """arcs: [(lo, len)] of every rank (needed_bins all-gathered); blobs: nranks x 128 bytes (P2P transport)."""
+        lo = (C.c_longlong * nranks)(*[a[0] for a in arcs])
+        ln = (C.c_longlong * nranks)(*[a[1] for a in arcs])
+        b = C.create_string_buffer(blobs, len(blobs)) if blobs else None
+        _lib.check(self.lib.ka9q_stream_mgpu_setup(self.h, transport, rank, nranks, lo, ln, b), "mgpu_setup")
+        self.mg_rank, self.mg_nranks = rank, nranks
+
+    def mgpu_input_range(self, first_block: int, nblocks: int):
+        a, n = C.c_longlong(), C.c_longlong()
+        _lib.check(self.lib.ka9q_stream_mgpu_input_range(self.h, first_block, nblocks, C.byref(a), C.byref(n)),
+                   "mgpu_input_range")
+        return a.value, n.value
+
+    def push_at(self, iq_ptr, first_sample: int, nsamples: int):
+        _lib.check(self.lib.ka9q_stream_push_at(self.h, iq_ptr, first_sample, nsamples), "push_at")
+
+    def mgpu_compute(self, nblocks: int, resident: bool = False):
+        _lib.check(self.lib.ka9q_stream_mgpu_compute(self.h, nblocks, 1 if resident else 0), "mgpu_compute")
+
+    def blocks_done(self) -> int:
+        return int(self.lib.ka9q_stream_blocks_done(self.h))
+
+    def mgpu_error(self) -> int:
+        return self.lib.ka9q_stream_mgpu_error(self.h)
 
     # -- introspection (parity tests) ----------------------------------------------------------------------
     def response(self, chan: int):

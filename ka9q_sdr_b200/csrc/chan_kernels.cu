@@ -50,6 +50,7 @@ struct FmShared {
 #if FM_TMA
   alignas(8) unsigned long long tma_bar;  // mbarrier the bulk copy completes on
 #endif
+  float4 tw2[FFT2048_TW2_FLOAT4];  // stage-2 twiddles of the 2048-point transform (fft2048.cuh)
   float red[16], red2[16];  // one scratch row per reduction of a channel-block: no barrier needed to recycle them
   unsigned good[32];
   float scal[8];
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
   __shared__ FmShared sh;
   const int t = threadIdx.x;
   const int2 wk = a.work[blockIdx.x];
+  fft2048_stage_tw2(sh.tw2, a.tw2048);
   if (t < 2) {
     const int c = t ? wk.y : wk.x;
     if (c >= 0) {
@@ -605,7 +607,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
           }
       }
       // the buffer's previous readers are a barrier behind us except after job 2 (its last stage just read it)
-      fft2048<+1>(v, sh.buf, a.tw2048, !FM_FEWER_BARRIERS || job == 3 || (FM_TMA == 1 && job < 2));
+      fft2048<+1>(v, sh.buf, a.tw2048, sh.tw2, !FM_FEWER_BARRIERS || job == 3 || (FM_TMA == 1 && job < 2));
       if (job < 2) {
         float ssq, samp, minsq;
         const int e = sh.ephase[h];
@@ -667,6 +669,7 @@ constexpr int AGC_ROW = 1024 + 1;  // floats per channel row: consecutive channe
 template <int AGC_G>
 struct AgcShared {
   float2 buf[NDEC];            // FFT exchange buffer
+  float4 tw2[FFT2048_TW2_FLOAT4];  // stage-2 twiddles of the 2048-point transform
   float amp[AGC_G][AGC_ROW];   // amplitude (AM: envelope s[n]); rows padded: lane g reads row g in the serial loops
   float qg[AGC_G][AGC_ROW];    // attack value headroom/x[n] precomputed in parallel; overwritten by gain[n]
   float red[16];
@@ -681,6 +684,8 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
   float2* ykeep = reinterpret_cast<float2*>(smraw + sizeof(AgcShared<AGC_G>));  // [AGC_G][1024], LINEAR only
   float* dcv = reinterpret_cast<float*>(smraw + sizeof(AgcShared<AGC_G>));      // [AGC_G][AGC_ROW], AM only
   const int t = threadIdx.x;
+  fft2048_stage_tw2(sh.tw2, a.tw2048);
+  __syncthreads();
   const int olen = OLEN_T ? OLEN_T : a.olen;
   const int first = NDEC - olen;
   const int jb = first >> 7, rem = first & 127;
@@ -719,7 +724,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
       } else {
         load_filtered16(v, X, a.N, bin, a.resp + (long long)c * NDEC);  // straight into the transform's registers
       }
-      fft2048<+1>(v, sh.buf, a.tw2048);
+      fft2048<+1>(v, sh.buf, a.tw2048, sh.tw2);
       // amplitudes (am.c:56-58, linear.c:256-261) and block power straight from the registers
       float sig = 0.f, noi = 0.f, dummy = 0.f;
       float* ampg = sh.amp[g];
@@ -915,6 +920,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
 
 struct FrontShared {
   float2 buf[NDEC];
+  float4 tw2[FFT2048_TW2_FLOAT4];  // stage-2 twiddles of the 2048-point transform
   float red[16];
 };
 
@@ -931,6 +937,8 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 8) agc_front_kernel(const Cha
   const bool isb = LINEAR && (a.params[c].flags & CH_ISB);
   const float2* H = a.resp + (long long)c * NDEC;
   float2 v[16];
+  fft2048_stage_tw2(sh.tw2, a.tw2048);
+  __syncthreads();
 #pragma unroll 1
   for (int b = 0; b < a.nblocks; b++) {
     const float2* X = a.spec + (long long)b * a.spec_stride;
@@ -941,7 +949,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 8) agc_front_kernel(const Cha
     } else {
       load_filtered16(v, X, a.N, bin, H);
     }
-    fft2048<+1>(v, sh.buf, a.tw2048);
+    fft2048<+1>(v, sh.buf, a.tw2048, sh.tw2);
     // amplitudes (am.c:56-58, linear.c:256-261) and block power straight from the registers
     const long long row = (long long)b * a.nwork + w;
     float* xr = a.agc_x + row * olen + (t - first);  // kept-sample index of row j is t - first + 128 j

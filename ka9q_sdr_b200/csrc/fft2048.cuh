@@ -24,6 +24,9 @@
 namespace k9 {
 
 constexpr int FFT2048_THREADS = 128;
+#ifndef FFT2048_TW_EARLY
+#define FFT2048_TW_EARLY 0
+#endif
 
 // Twiddle table layout (FFT2048_TW_FLOAT2 float2 entries, built by fft2048_fill_twiddles on the host), laid out so that
 // the lanes of a warp read CONSECUTIVE addresses (the L1 data pipe was the kernel's limiter, and a row per thread costs
@@ -31,9 +34,12 @@ constexpr int FFT2048_THREADS = 128;
 //   stage 1, butterfly p in [0,256), twiddles W_2048^(p*j), j = 1..7 (j = 0 is 1 and is not stored):
 //     float4 A[jj][p], jj in [0,3): (W^(p(2jj+1)), W^(p(2jj+2)))      at float2 offset 2*(256*jj + p)
 //     float2 B[p]:                   W^(7p)                           at float2 offset 1536 + p
-//   stage 2, butterfly p' = t >> 3 in [0,16), twiddles W_256^(p'*j), j = 0..15: the four p' of a warp side by side,
-//     float4 C[w][jj][sub], p' = 4w + sub: (W^(p'*2jj), W^(p'*(2jj+1)))  at float2 offset 1792 + 2*((8w + jj)*4 + sub)
-//     (a warp's 128-bit load touches one 64-byte segment)
+//   stage 2, butterfly p' = t >> 3 in [0,16), twiddles W_256^(p'*j), j = 0..15: 2 KB that every thread of every CTA reads
+//     in full 128-byte rows; they are copied ONCE per CTA into shared memory (fft2048_stage_tw2) and read from there:
+//     float4 C[jj][p']: (W^(p'*2jj), W^(p'*(2jj+1)))                  at float2 offset 1792 + 2*(16 jj + p')
+//     the four p' of a warp sit side by side, so a warp's 128-bit shared load covers one 64-byte segment (one wavefront;
+//     the same load from global memory returns 32 x 16 bytes through the L1 data stage = 4 wavefronts, and these rows
+//     were 512 of the FM kernel's 5640 L1 wavefronts per pair-block after the stage-1 change)
 // Forward sign (exp(-2*pi*i...)); conjugated on use when SIGN=+1. Same values and the same arithmetic as a row-per-
 // thread table: results are bit-identical.
 constexpr int FFT2048_TW_FLOAT2 = 1792 + 256;
@@ -45,15 +51,35 @@ __device__ __forceinline__ float2 tw_mul(float2 a, float wx, float wy) {
   return cmul_xy(a, wx, SIGN > 0 ? -wy : wy);
 }
 
+constexpr int FFT2048_TW2_FLOAT4 = 128;  // shared-memory copy of the stage-2 table
+
+// once per CTA (128 threads), before the first transform; the caller's next barrier publishes it
+__device__ __forceinline__ void fft2048_stage_tw2(float4* __restrict__ tw2s, const float2* __restrict__ tw) {
+  tw2s[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(tw + FFT2048_TW_C) + threadIdx.x);
+}
+
 template <int SIGN>
 __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb, const float2* __restrict__ tw,
-                                        bool war_sync = true) {
+                                        const float4* __restrict__ tw2s, bool war_sync = true) {
   const int t = threadIdx.x;
   // ---- stage 1: two radix-8 butterflies, p = t + 128e; y1[8p + j] = w_2048^(p j) * DFT8 ----
 #pragma unroll
   for (int e = 0; e < 2; e++) {
-    Dft<8, SIGN>::run(&v[8 * e]);
     const float4* A = reinterpret_cast<const float4*>(tw) + (t + 128 * e);
+#if FFT2048_TW_EARLY
+    // twiddle loads issued ahead of the butterfly so their latency hides under it (costs 14 registers)
+    float4 w[3];
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) w[jj] = __ldg(A + 256 * jj);
+    const float2 w7 = __ldg(tw + FFT2048_TW_B + t + 128 * e);
+    Dft<8, SIGN>::run(&v[8 * e]);
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) {
+      v[8 * e + 2 * jj + 1] = tw_mul<SIGN>(v[8 * e + 2 * jj + 1], w[jj].x, w[jj].y);
+      v[8 * e + 2 * jj + 2] = tw_mul<SIGN>(v[8 * e + 2 * jj + 2], w[jj].z, w[jj].w);
+    }
+#else
+    Dft<8, SIGN>::run(&v[8 * e]);
 #pragma unroll
     for (int jj = 0; jj < 3; jj++) {
       const float4 w = __ldg(A + 256 * jj);
@@ -61,6 +87,7 @@ __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb
       v[8 * e + 2 * jj + 2] = tw_mul<SIGN>(v[8 * e + 2 * jj + 2], w.z, w.w);
     }
     const float2 w7 = __ldg(tw + FFT2048_TW_B + t + 128 * e);
+#endif
     v[8 * e + 7] = tw_mul<SIGN>(v[8 * e + 7], w7.x, w7.y);
   }
   if (war_sync) __syncthreads();  // WAR: previous users of the buffer are done (CTA-uniform flag)
@@ -85,10 +112,10 @@ __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb
   }
   Dft<16, SIGN>::run(v);
   {
-    const float4* row = reinterpret_cast<const float4*>(tw + FFT2048_TW_C) + 32 * (t >> 5) + ((t >> 3) & 3);
+    const float4* row = tw2s + (t >> 3);
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) {
-      const float4 w = __ldg(row + 4 * jj);
+      const float4 w = row[16 * jj];
       if (jj > 0) v[2 * jj] = tw_mul<SIGN>(v[2 * jj], w.x, w.y);
       v[2 * jj + 1] = tw_mul<SIGN>(v[2 * jj + 1], w.z, w.w);
     }
@@ -132,7 +159,7 @@ inline void fft2048_fill_twiddles(float2* tw) {
   }
   for (int pp = 0; pp < 16; pp++)
     for (int jj = 0; jj < 8; jj++) {
-      const int idx = FFT2048_TW_C + 2 * ((8 * (pp >> 2) + jj) * 4 + (pp & 3));
+      const int idx = FFT2048_TW_C + 2 * (16 * jj + pp);
       tw[idx] = w(pp * 2 * jj, 256);
       tw[idx + 1] = w(pp * (2 * jj + 1), 256);
     }

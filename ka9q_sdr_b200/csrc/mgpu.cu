@@ -1,0 +1,377 @@
+// Channel-sharded multi-GPU channelizer (BASELINE.json north_star: "channels are sharded across the 8 GPUs
+// of one box"). One process per GPU; every rank holds a contiguous (in carrier frequency) share of the channels and never
+// moves channel state. Per batch of nblocks 20 ms blocks:
+//
+//   1. the forward FFT is sharded BY BLOCK: rank q transforms blocks [q*nb/G, (q+1)*nb/G) of the batch (it needs the int16
+//      samples of those blocks plus the M-1 samples of overlap in front of them, nothing else);
+//   2. exchange: a rank's channels only read the arc [min bin - 1023, max bin + 1024] of the N-bin spectrum (1/G of it plus
+//      a 2048-bin halo), so the producer of a block sends every peer just that peer's arc — 21 MB x (1/G + halo) per block
+//      and peer instead of the 21 MB a broadcast moves. Two transports:
+//        KA9Q_MGPU_P2P   (default) a copy kernel of this library stores the arcs straight into the peers' spectrum buffers
+//                        over NVLink (peer memory mapped with CUDA IPC), then raises a per-producer sequence flag in the
+//                        peer's memory; the consumer's channel stream spins on its flags in a one-warp kernel. Flow
+//                        control in the other direction (the consumer has finished reading buffer p) uses the same flags.
+//                        No host round trip, no collective library on the data path.
+//        KA9Q_MGPU_NCCL  grouped ncclSend/ncclRecv of the same arcs (cross-check and fallback).
+//   3. every rank runs its channel kernels on its own share.
+//
+// The spectrum is double-buffered, so the FFT + exchange of batch k+1 overlap the channel kernels of batch k.
+// Results equal the single-GPU run: AM / linear bit for bit, FM within 1 LSB where the pair partner differs.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "stream_priv.cuh"
+
+namespace {
+
+struct CopyJob {  // 16-byte units
+  const int4* src;
+  int4* dst;
+  long long n16;
+};
+
+constexpr int SCATTER_THREADS = 256;
+constexpr long long SPIN_TIMEOUT_CYCLES = 6000000000ll;  // ~3 s: a dead peer must not hang the GPU
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Stores the arcs of this rank's freshly transformed blocks into the peers' spectrum buffers (NVLink peer stores), then —
+// once every CTA's stores are performed at system scope — raises ready[p][me] = seq in every peer's flag block.
+__global__ void __launch_bounds__(SCATTER_THREADS) mgpu_scatter_kernel(const CopyJob* __restrict__ jobs, int njobs,
+                                                                       unsigned* counter, MgpuFlags* const* peer_flags,
+                                                                       int nranks, int me, int p, int seq) {
+  for (int j = 0; j < njobs; j++) {
+    const CopyJob job = jobs[j];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < job.n16; i += (long long)gridDim.x * blockDim.x)
+      job.dst[i] = __ldg(job.src + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) *counter = 0;
+    __threadfence_system();
+    if (threadIdx.x < nranks && threadIdx.x != me) st_release_sys(&peer_flags[threadIdx.x]->ready[p][me], seq);
+  }
+}
+
+// one warp: lane r waits until flags[r] >= want (r != me, r < nranks)
+__global__ void mgpu_wait_kernel(MgpuFlags* flags, int which /* 0 ready, 1 freed */, int p, int nranks, int me, int want) {
+  const int r = threadIdx.x;
+  if (r >= nranks || r == me) return;
+  const int* f = which ? &flags->freed[p][r] : &flags->ready[p][r];
+  const long long t0 = clock64();
+  while (ld_acquire_sys(f) < want) {
+    __nanosleep(200);
+    if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
+      flags->error = 1;
+      break;
+    }
+  }
+}
+
+// consumer -> producers: this rank has finished reading its spectrum buffer p for batch seq
+__global__ void mgpu_signal_free_kernel(MgpuFlags* const* peer_flags, int nranks, int me, int p, int seq) {
+  const int r = threadIdx.x;
+  if (r >= nranks || r == me) return;
+  __threadfence_system();
+  st_release_sys(&peer_flags[r]->freed[p][me], seq);
+}
+
+struct IpcBlob {  // what ka9q_stream_mgpu_export writes (128 bytes)
+  cudaIpcMemHandle_t spec, flags;
+};
+static_assert(sizeof(IpcBlob) == 128, "IPC blob layout");
+
+}  // namespace
+
+void mgpu_release(ka9q_stream* s) {
+  for (int r = 0; r < K9_MAX_RANKS; r++) {
+    if (s->mg_ipc_opened[r]) {
+      if (s->mg_peer_spec[r]) cudaIpcCloseMemHandle(s->mg_peer_spec[r]);
+      if (s->mg_peer_flags[r]) cudaIpcCloseMemHandle(s->mg_peer_flags[r]);
+    }
+    s->mg_peer_spec[r] = nullptr;
+    s->mg_peer_flags[r] = nullptr;
+    s->mg_ipc_opened[r] = false;
+  }
+  if (s->d_flags) cudaFree(s->d_flags);
+  if (s->d_mg_jobs) cudaFree(s->d_mg_jobs);
+  if (s->d_mg_counter) cudaFree(s->d_mg_counter);
+  if (s->d_mg_peer_flag_ptrs) cudaFree(s->d_mg_peer_flag_ptrs);
+  s->d_flags = nullptr;
+  s->d_mg_jobs = nullptr;
+  s->d_mg_counter = nullptr;
+  s->d_mg_peer_flag_ptrs = nullptr;
+  s->mg_nranks = 0;
+}
+
+extern "C" {
+
+// The arc of the spectrum this rank's channels read: bins [lo, lo + len) mod N, 16-bin (128-byte) aligned. Channels are
+// taken on the signed grid (bin > N/2 counts as bin - N), which is how a frequency-contiguous shard is contiguous.
+int ka9q_stream_needed_bins(ka9q_stream* s, long long* lo, long long* len) {
+  K9_CHECK(s && s->committed && lo && len, "bad argument");
+  const long long N = s->N;
+  long long mn = 0, mx = 0;
+  bool first = true;
+  for (const ka9q_chan_params& p : s->chans) {
+    long long b = p.bin > N / 2 ? p.bin - N : p.bin;
+    if (first || b < mn) mn = b;
+    if (first || b > mx) mx = b;
+    first = false;
+  }
+  long long a = mn - 1023, e = mx + 1024 + 1;  // [a, e)
+  a = (a >= 0 ? a / 16 : -((-a + 15) / 16)) * 16;
+  e = (e >= 0 ? (e + 15) / 16 : -((-e) / 16)) * 16;
+  long long n = e - a;
+  if (n >= N) {
+    *lo = 0;
+    *len = N;
+  } else {
+    *lo = ((a % N) + N) % N;
+    *len = n;
+  }
+  return 0;
+}
+
+// 128-byte handle blob of this rank's spectrum buffers and flag block, to be all-gathered by the host plumbing
+int ka9q_stream_mgpu_export(ka9q_stream* s, void* blob128) {
+  K9_CHECK(s && s->committed && blob128, "bad argument");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  if (!s->d_flags) {
+    K9_CUDA(cudaMalloc(&s->d_flags, sizeof(MgpuFlags)));
+    K9_CUDA(cudaMemset(s->d_flags, 0, sizeof(MgpuFlags)));
+  }
+  IpcBlob b;
+  K9_CUDA(cudaIpcGetMemHandle(&b.spec, s->d_spec));
+  K9_CUDA(cudaIpcGetMemHandle(&b.flags, s->d_flags));
+  memcpy(blob128, &b, sizeof(b));
+  return 0;
+}
+
+// transport: KA9Q_MGPU_NCCL (needs ka9q_stream_nccl_init first) or KA9Q_MGPU_P2P (needs the peers' blobs).
+// lo_all / len_all: every rank's ka9q_stream_needed_bins. blobs: nranks x 128 bytes (P2P only, may be NULL for NCCL).
+int ka9q_stream_mgpu_setup(ka9q_stream* s, int transport, int rank, int nranks, const long long* lo_all,
+                           const long long* len_all, const void* blobs) {
+  K9_CHECK(s && s->committed && lo_all && len_all, "bad argument");
+  K9_CHECK(nranks >= 1 && nranks <= K9_MAX_RANKS && rank >= 0 && rank < nranks, "bad rank / nranks");
+  K9_CHECK(transport == KA9Q_MGPU_NCCL || transport == KA9Q_MGPU_P2P, "bad transport");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  if (transport == KA9Q_MGPU_NCCL)
+    K9_CHECK(nranks == 1 || (s->nccl_comm && s->nccl_nranks == nranks && s->nccl_rank == rank && p_ncclSend && p_ncclRecv &&
+                             p_ncclGroupStart && p_ncclGroupEnd),
+             "NCCL transport: call ka9q_stream_nccl_init(rank, nranks) first");
+  const long long N = s->N;
+  s->mg_need.assign(nranks, {});
+  for (int r = 0; r < nranks; r++) {
+    long long lo = lo_all[r], len = len_all[r];
+    K9_CHECK(lo >= 0 && lo < N && len > 0 && len <= N && lo % 16 == 0 && len % 16 == 0, "bad arc for rank %d", r);
+    if (lo + len <= N) {
+      s->mg_need[r].push_back({lo, len});
+    } else {
+      s->mg_need[r].push_back({lo, N - lo});
+      s->mg_need[r].push_back({0, lo + len - N});
+    }
+  }
+  s->mg_rank = rank;
+  s->mg_nranks = nranks;
+  s->mg_transport = transport;
+  s->mg_seq = 0;
+  if (transport == KA9Q_MGPU_P2P && nranks > 1) {
+    K9_CHECK(blobs, "P2P transport needs the peers' handle blobs");
+    K9_CHECK(s->d_flags, "call ka9q_stream_mgpu_export before setup");
+    std::vector<MgpuFlags*> fl(K9_MAX_RANKS, nullptr);
+    for (int r = 0; r < nranks; r++) {
+      if (r == rank) {
+        s->mg_peer_spec[r] = s->d_spec;
+        s->mg_peer_flags[r] = s->d_flags;
+      } else {
+        IpcBlob b;
+        memcpy(&b, (const char*)blobs + (size_t)r * sizeof(IpcBlob), sizeof(b));
+        void *ps = nullptr, *pf = nullptr;
+        K9_CUDA(cudaIpcOpenMemHandle(&ps, b.spec, cudaIpcMemLazyEnablePeerAccess));
+        K9_CUDA(cudaIpcOpenMemHandle(&pf, b.flags, cudaIpcMemLazyEnablePeerAccess));
+        s->mg_peer_spec[r] = (float2*)ps;
+        s->mg_peer_flags[r] = (MgpuFlags*)pf;
+        s->mg_ipc_opened[r] = true;
+      }
+      fl[r] = s->mg_peer_flags[r];
+    }
+    K9_CUDA(cudaMalloc(&s->d_mg_peer_flag_ptrs, sizeof(MgpuFlags*) * K9_MAX_RANKS));
+    K9_CUDA(cudaMemcpy(s->d_mg_peer_flag_ptrs, fl.data(), sizeof(MgpuFlags*) * K9_MAX_RANKS, cudaMemcpyHostToDevice));
+    K9_CUDA(cudaMalloc(&s->d_mg_counter, sizeof(unsigned)));
+    K9_CUDA(cudaMemset(s->d_mg_counter, 0, sizeof(unsigned)));
+    // copy-job lists, one per spectrum buffer parity: (my blocks) x (peers) x (pieces of the peer's arc)
+    K9_CHECK(s->cfg.max_blocks % nranks == 0, "max_blocks must be a multiple of the number of ranks");
+  }
+  return 0;
+}
+
+// Sample range (absolute stream positions) this rank has to hold in its ring to transform its share of the batch that
+// starts at block `first_block`: its blocks plus the M-1 samples of overlap in front of them.
+int ka9q_stream_mgpu_input_range(ka9q_stream* s, long long first_block, int nblocks, long long* first_sample,
+                                 long long* nsamples) {
+  K9_CHECK(s && s->committed && first_sample && nsamples, "bad argument");
+  const int G = s->mg_nranks > 0 ? s->mg_nranks : 1;
+  K9_CHECK(nblocks >= 1 && nblocks % G == 0, "nblocks must be a multiple of the number of ranks");
+  const long long L = s->cfg.L, M = s->cfg.M;
+  const int cnt = nblocks / G, bf = s->mg_rank * cnt;
+  long long a = (first_block + bf) * L - (M - 1), e = (first_block + bf + cnt) * L;
+  if (a < 0) a = 0;
+  *first_sample = a;
+  *nsamples = e - a;
+  return 0;
+}
+
+// H2D copy of samples [first_sample, first_sample + nsamples) of the stream to their place in the device ring (the
+// block-sharded forward FFT reads only part of every batch). Async on the copy stream, like ka9q_stream_push.
+int ka9q_stream_push_at(ka9q_stream* s, const void* iq, long long first_sample, long long nsamples) {
+  K9_CHECK(s && s->committed && iq && first_sample >= 0 && nsamples > 0, "bad argument");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  const long long end = first_sample + nsamples;
+  K9_CHECK(end - s->block0 * (long long)s->cfg.L <= 2LL * s->cfg.max_blocks * s->cfg.L,
+           "push would overwrite samples that have not been computed yet");
+  K9_CUDA(cudaStreamWaitEvent(s->s_in, s->e_comp_done[s->comp_parity], 0));
+  long long pos = (first_sample + (s->cfg.M - 1)) % s->ring_cap, done = 0;
+  while (done < nsamples) {
+    const long long chunk = std::min(nsamples - done, s->ring_cap - pos);
+    K9_CUDA(cudaMemcpyAsync((char*)s->d_ring + pos * s->bytes_per_samp, (const char*)iq + done * s->bytes_per_samp,
+                            (size_t)chunk * s->bytes_per_samp, cudaMemcpyHostToDevice, s->s_in));
+    done += chunk;
+    pos = (pos + chunk) % s->ring_cap;
+  }
+  if (end > s->pushed) s->pushed = end;
+  K9_CUDA(cudaEventRecord(s->e_pushed, s->s_in));
+  return 0;
+}
+
+static int exchange_nccl(ka9q_stream* s, int nblocks, int p) {
+  const int G = s->mg_nranks, me = s->mg_rank, cnt = nblocks / G;
+  float2* buf = spec_buf(s, p);
+  int r = p_ncclGroupStart();
+  for (int peer = 0; peer < G && r == 0; peer++) {
+    if (peer == me) continue;
+    for (int b = me * cnt; b < (me + 1) * cnt && r == 0; b++)
+      for (const MgpuSeg& sg : s->mg_need[peer])
+        if (r == 0) r = p_ncclSend(buf + (size_t)b * s->N + sg.lo, (size_t)2 * sg.len, /*ncclFloat32*/ 7, peer, (k9_ncclComm_t)s->nccl_comm, s->s_fft);
+    for (int b = peer * cnt; b < (peer + 1) * cnt && r == 0; b++)
+      for (const MgpuSeg& sg : s->mg_need[me])
+        if (r == 0) r = p_ncclRecv(buf + (size_t)b * s->N + sg.lo, (size_t)2 * sg.len, 7, peer, (k9_ncclComm_t)s->nccl_comm, s->s_fft);
+  }
+  const int r2 = p_ncclGroupEnd();
+  if (r == 0) r = r2;
+  K9_CHECK(r == 0, "NCCL sub-band exchange: %s", p_ncclGetErrorString ? p_ncclGetErrorString(r) : "error");
+  return 0;
+}
+
+static int exchange_p2p(ka9q_stream* s, int nblocks, int p, int seq) {
+  const int G = s->mg_nranks, me = s->mg_rank, cnt = nblocks / G;
+  // copy-job list of this (parity, nblocks) shape, built once and cached on the device
+  if (s->mg_jobs_nblocks != nblocks) {
+    std::vector<CopyJob> jobs[2];
+    for (int par = 0; par < 2; par++)
+      for (int peer = 0; peer < G; peer++) {
+        if (peer == me) continue;
+        for (int b = me * cnt; b < (me + 1) * cnt; b++)
+          for (const MgpuSeg& sg : s->mg_need[peer]) {
+            const size_t off = ((size_t)par * s->cfg.max_blocks + b) * s->N + sg.lo;
+            jobs[par].push_back({(const int4*)(s->d_spec + off), (int4*)(s->mg_peer_spec[peer] + off), sg.len / 2});
+          }
+      }
+    s->mg_njobs = (int)jobs[0].size();
+    if (s->d_mg_jobs) cudaFree(s->d_mg_jobs);
+    s->d_mg_jobs = nullptr;
+    if (s->mg_njobs) {
+      K9_CUDA(cudaMalloc(&s->d_mg_jobs, sizeof(CopyJob) * 2 * s->mg_njobs));
+      K9_CUDA(cudaMemcpy(s->d_mg_jobs, jobs[0].data(), sizeof(CopyJob) * s->mg_njobs, cudaMemcpyHostToDevice));
+      K9_CUDA(cudaMemcpy((CopyJob*)s->d_mg_jobs + s->mg_njobs, jobs[1].data(), sizeof(CopyJob) * s->mg_njobs, cudaMemcpyHostToDevice));
+    }
+    s->mg_jobs_nblocks = nblocks;
+  }
+  // the peers have finished reading their buffer p of two batches ago
+  if (seq > 2) mgpu_wait_kernel<<<1, 32, 0, s->s_fft>>>(s->d_flags, 1, p, G, me, seq - 2);
+  // a few CTAs per SM is plenty for NVLink (~0.8 TB/s) and leaves the SMs to the channel kernels of the previous batch
+  mgpu_scatter_kernel<<<148, SCATTER_THREADS, 0, s->s_fft>>>((const CopyJob*)s->d_mg_jobs + (size_t)p * s->mg_njobs, s->mg_njobs,
+                                                            s->d_mg_counter, s->d_mg_peer_flag_ptrs, G, me, p, seq);
+  K9_CHECK(cudaGetLastError() == cudaSuccess, "scatter kernel launch failed");
+  return 0;
+}
+
+// One batch in channel-sharded mode: forward FFT of this rank's blocks, exchange of the arcs, channel kernels.
+// resident != 0: re-run the most recently pushed batch (every rank holds the whole batch in its ring; benchmarks with the
+// input already in HBM); resident == 0: streaming (push / push_at beforehand).
+int ka9q_stream_mgpu_compute(ka9q_stream* s, int nblocks, int resident) {
+  K9_CHECK(s && s->committed && s->mg_nranks >= 1, "call ka9q_stream_mgpu_setup first");
+  const int G = s->mg_nranks, me = s->mg_rank;
+  K9_CHECK(nblocks >= 1 && nblocks <= s->cfg.max_blocks && nblocks % G == 0, "nblocks must be a multiple of the number of ranks");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  const int cnt = nblocks / G, bf = me * cnt;
+  long long first_block;
+  if (resident) {
+    first_block = s->pushed / s->cfg.L - nblocks;
+    K9_CHECK(first_block >= 0, "not enough samples resident in the ring");
+    if (s->phase_block < first_block) s->phase_block = first_block;
+  } else {
+    first_block = s->block0;
+    K9_CHECK((first_block + bf + cnt) * (long long)s->cfg.L <= s->pushed, "compute ahead of pushed samples");
+  }
+  const int p = s->spec_wr;
+  const int seq = ++s->mg_seq;
+  if (issue_fft(s, first_block, bf, cnt)) return -1;
+  if (G > 1) {
+    TimedRegion tr(s, TC_BCAST, s->s_fft);
+    if (s->mg_transport == KA9Q_MGPU_NCCL) {
+      if (exchange_nccl(s, nblocks, p)) return -1;
+    } else {
+      if (exchange_p2p(s, nblocks, p, seq)) return -1;
+    }
+  }
+  if (publish_spectrum(s)) return -1;
+  if (G > 1 && s->mg_transport == KA9Q_MGPU_P2P) {
+    // the channel stream waits for every producer's arcs (issue_channels makes s_comp wait for e_spec_ready first)
+    s->mg_wait_ready = seq;
+  }
+  if (issue_channels(s, nblocks)) return -1;
+  if (G > 1 && s->mg_transport == KA9Q_MGPU_P2P) {
+    mgpu_signal_free_kernel<<<1, 32, 0, s->s_comp>>>(s->d_mg_peer_flag_ptrs, G, me, p, seq);
+    K9_CHECK(cudaGetLastError() == cudaSuccess, "signal kernel launch failed");
+    // later FFTs into buffer p also wait for this signal having been sent (keeps seq order on the wire)
+    K9_CUDA(cudaEventRecord(s->e_spec_free[p], s->s_comp));
+  }
+  if (resident)
+    s->block0 = s->pushed / s->cfg.L;
+  else
+    s->block0 += nblocks;
+  return 0;
+}
+
+// P2P transport: has a wait on a peer flag timed out (a peer died)? Valid after ka9q_stream_sync.
+int ka9q_stream_mgpu_error(ka9q_stream* s) {
+  K9_CHECK(s && s->committed, "bad argument");
+  if (!s->d_flags) return 0;
+  int e = 0;
+  K9_CUDA(cudaMemcpy(&e, &s->d_flags->error, sizeof(int), cudaMemcpyDeviceToHost));
+  return e;
+}
+
+}  // extern "C"
+
+// called by issue_channels (stream.cu) on the channel stream, after it has been made to wait for e_spec_ready[p]
+int mgpu_wait_ready(ka9q_stream* s, int p) {
+  if (s->mg_wait_ready <= 0) return 0;
+  mgpu_wait_kernel<<<1, 32, 0, s->s_comp>>>(s->d_flags, 0, p, s->mg_nranks, s->mg_rank, s->mg_wait_ready);
+  s->mg_wait_ready = 0;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

