@@ -214,6 +214,11 @@ int ka9q_stream_commit(ka9q_stream *s);
 /* Re-design one channel's filter after commit (the UI path: display.c:163-177). */
 int ka9q_stream_set_filter(ka9q_stream *s, int chan, float low, float high, float kaiser_beta);
 
+/* Noise-density estimate compute_n0 (radio.c:383-425; fm.c:78-82, am.c:46-49, linear.c:123-126) for every channel and
+ * block, computed once per stream on the device (csrc/n0.cu). Enable before commit; rows are fetched like the PCM. */
+int ka9q_stream_enable_n0(ka9q_stream *s, int enable);
+int ka9q_stream_fetch_n0(ka9q_stream *s, int nblocks, float *raw /* compute_n0() per block */,
+                         float *smooth /* demod->sig.n0 after each block */);
 int ka9q_stream_num_channels(const ka9q_stream *s);
 /* int16 units per block row of the PCM output, and a channel's offset / channel count inside the row */
 long long ka9q_stream_pcm_stride(const ka9q_stream *s);

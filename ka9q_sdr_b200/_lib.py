@@ -66,6 +66,7 @@ EXPORTED = [
     "ka9q_rtp_process", "ka9q_pcm_packetise", "ka9q_stream_wait_fetched", "ka9q_status_encode_signals",
     "ka9q_stream_needed_bins", "ka9q_stream_mgpu_export", "ka9q_stream_mgpu_setup", "ka9q_stream_mgpu_input_range",
     "ka9q_stream_push_at", "ka9q_stream_mgpu_compute", "ka9q_stream_mgpu_error", "ka9q_stream_blocks_done",
+    "ka9q_stream_enable_n0", "ka9q_stream_fetch_n0",
 ]
 
 
@@ -128,6 +129,8 @@ def lib():
     L.ka9q_stream_push_at.argtypes = [vp, vp, cll, cll]
     L.ka9q_stream_mgpu_compute.argtypes = [vp, ci, ci]
     L.ka9q_stream_mgpu_error.argtypes = [vp]
+    L.ka9q_stream_enable_n0.argtypes = [vp, ci]
+    L.ka9q_stream_fetch_n0.argtypes = [vp, ci, vp, vp]
     L.ka9q_stream_blocks_done.argtypes = [vp]
     L.ka9q_stream_blocks_done.restype = cll
     L.ka9q_host_alloc.argtypes = [C.c_size_t]

@@ -88,6 +88,20 @@ class Channelizer:
         self.channels.append(int(p.channels) if m.demod_type == LINEAR_DEMOD else 1)
         return idx
 
+    def enable_n0(self, enable: bool = True):
+        """compute_n0 (radio.c:383-425) for every channel and block; call before commit."""
+        _lib.check(self.lib.ka9q_stream_enable_n0(self.h, 1 if enable else 0), "enable_n0")
+        self.n0_enabled = enable
+
+    def fetch_n0(self, nblocks: int):
+        """(raw, smoothed) noise density of the last computed batch, [nblocks, nchan] float32 each; synchronises."""
+        raw = np.empty((nblocks, self.nchan), dtype=np.float32)
+        sm = np.empty((nblocks, self.nchan), dtype=np.float32)
+        _lib.check(self.lib.ka9q_stream_fetch_n0(self.h, nblocks, raw.ctypes.data_as(C.c_void_p),
+                                                 sm.ctypes.data_as(C.c_void_p)), "fetch_n0")
+        self.sync()
+        return raw, sm
+
     def commit(self):
         _lib.check(self.lib.ka9q_stream_commit(self.h), "ka9q_stream_commit")
         self.committed = True

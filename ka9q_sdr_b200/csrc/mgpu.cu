@@ -51,8 +51,18 @@ __global__ void __launch_bounds__(SCATTER_THREADS) mgpu_scatter_kernel(const Cop
                                                                        int nranks, int me, int p, int seq) {
   for (int j = 0; j < njobs; j++) {
     const CopyJob job = jobs[j];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < job.n16; i += (long long)gridDim.x * blockDim.x)
-      job.dst[i] = __ldg(job.src + i);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // four independent 16-byte loads in flight per thread before the (posted) peer stores
+    for (; i + 3 * stride < job.n16; i += 4 * stride) {
+      const int4 a = __ldg(job.src + i), b = __ldg(job.src + i + stride), c = __ldg(job.src + i + 2 * stride),
+                 d = __ldg(job.src + i + 3 * stride);
+      job.dst[i] = a;
+      job.dst[i + stride] = b;
+      job.dst[i + 2 * stride] = c;
+      job.dst[i + 3 * stride] = d;
+    }
+    for (; i < job.n16; i += stride) job.dst[i] = __ldg(job.src + i);
   }
   __threadfence_system();
   __syncthreads();

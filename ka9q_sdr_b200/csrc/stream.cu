@@ -285,6 +285,29 @@ static int commit_impl(ka9q_stream* s) {
   K9_CUDA(cudaMalloc(&s->d_status, sizeof(ChanStatus) * 2 * (size_t)B * K));
   K9_CUDA(cudaMemset(s->d_status, 0, sizeof(ChanStatus) * 2 * (size_t)B * K));
 
+  if (s->n0_enabled) {
+    K9_CUDA(cudaStreamCreateWithFlags(&s->s_n0, cudaStreamNonBlocking));
+    K9_CUDA(cudaEventCreateWithFlags(&s->e_n0, cudaEventDisableTiming));
+    K9_CUDA(cudaMalloc(&s->d_n0_chan, sizeof(N0Chan) * K));
+    K9_CUDA(cudaMalloc(&s->d_n0_P, sizeof(float) * (size_t)B * N));
+    K9_CUDA(cudaMalloc(&s->d_n0_partial, sizeof(double) * (size_t)B * N0_POWER_CTAS));
+    K9_CUDA(cudaMalloc(&s->d_n0_blk, sizeof(N0Block) * B));
+    K9_CUDA(cudaMalloc(&s->d_n0_T, sizeof(float) * (size_t)B * K));
+    K9_CUDA(cudaMalloc(&s->d_n0_list, sizeof(float) * (size_t)B * N0_LIST_CAP));
+    K9_CUDA(cudaMalloc(&s->d_n0_raw, sizeof(float) * 2 * (size_t)B * K));     // double-buffered like the PCM / status
+    K9_CUDA(cudaMalloc(&s->d_n0_smooth, sizeof(float) * 2 * (size_t)B * K));
+    K9_CUDA(cudaMalloc(&s->d_n0_state, sizeof(float) * K));
+    K9_CUDA(cudaMemset(s->d_n0_state, 0, sizeof(float) * K));  // struct demod is zero-initialised: sig.n0 starts at 0
+    std::vector<N0Chan> nc(K);
+    for (int c = 0; c < K; c++) {
+      const ka9q_chan_params& p = s->chans[c];
+      nc[c].bin = (int)p.bin;
+      n0_passband_bins(N, s->cfg.samprate, p.low, p.high, &nc[c].nlo, &nc[c].nhi);
+      nc[c].alpha = p.demod_type == KA9Q_FM_DEMOD ? 0.01f : 0.001f;
+    }
+    K9_CUDA(cudaMemcpy(s->d_n0_chan, nc.data(), sizeof(N0Chan) * K, cudaMemcpyHostToDevice));
+  }
+
   // parameter blocks, PCM layout, work lists
   s->h_params.resize(K);
   std::vector<ChanState> st(K);
@@ -404,6 +427,28 @@ int ka9q_stream_set_filter(ka9q_stream* s, int chan, float low, float high, floa
     s->h_params[chan].fm_gain = (p.headroom * M_1_PI * dsamprate) / fabsf(p.low - p.high);
     K9_CUDA(cudaMemcpy(s->d_params + chan, &s->h_params[chan], sizeof(ChanParams), cudaMemcpyHostToDevice));
   }
+  return 0;
+}
+
+// Noise-density estimate (compute_n0, radio.c:383-425) for every channel and block; call before commit.
+int ka9q_stream_enable_n0(ka9q_stream* s, int enable) {
+  K9_CHECK(s, "null argument");
+  K9_CHECK(!s->committed, "ka9q_stream_enable_n0 must be called before commit");
+  s->n0_enabled = enable != 0;
+  return 0;
+}
+
+// n0 rows of the last computed batch (like ka9q_stream_fetch: async on the output stream, ka9q_stream_sync / wait_fetch
+// afterwards). raw: compute_n0() of each block; smooth: demod->sig.n0 after each block. [nblocks][nchan] floats each.
+int ka9q_stream_fetch_n0(ka9q_stream* s, int nblocks, float* raw, float* smooth) {
+  K9_CHECK(s && s->committed && s->n0_enabled, "n0 not enabled");
+  K9_CHECK(nblocks >= 1 && nblocks <= s->cfg.max_blocks, "nblocks out of range");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  K9_CUDA(cudaStreamWaitEvent(s->s_out, s->e_comp_done[s->comp_parity], 0));
+  const size_t off = (size_t)s->comp_parity * s->cfg.max_blocks * s->chans.size(), n = sizeof(float) * (size_t)nblocks * s->chans.size();
+  if (raw) K9_CUDA(cudaMemcpyAsync(raw, s->d_n0_raw + off, n, cudaMemcpyDeviceToHost, s->s_out));
+  if (smooth) K9_CUDA(cudaMemcpyAsync(smooth, s->d_n0_smooth + off, n, cudaMemcpyDeviceToHost, s->s_out));
+  K9_CUDA(cudaEventRecord(s->e_fetched[s->comp_parity], s->s_out));
   return 0;
 }
 
@@ -580,6 +625,31 @@ int issue_channels(ka9q_stream* s, int nblocks) {
     TimedRegion tr(s, TC_FM, s->s_comp);
     K9_CHECK(launch_fm(a, s->s_comp, s->n_am + s->n_lin > 0) == 0, "fm kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
+  if (s->n0_enabled) {
+    // K6 beside the channel kernels: reads the same spectrum buffer, writes the n0 rows of this batch
+    K9_CUDA(cudaStreamWaitEvent(s->s_n0, s->e_fork, 0));
+    N0Launch n;
+    n.spec = a.spec;
+    n.spec_stride = s->N;
+    n.N = s->N;
+    n.samprate = s->cfg.samprate;
+    n.nblocks = nblocks;
+    n.nchan = (int)s->chans.size();
+    n.chan = s->d_n0_chan;
+    n.P = s->d_n0_P;
+    n.partial = s->d_n0_partial;
+    n.blk = s->d_n0_blk;
+    n.T = s->d_n0_T;
+    n.list = s->d_n0_list;
+    n.list_cap = N0_LIST_CAP;
+    const int wbuf = s->comp_parity ^ 1;
+    n.n0_raw = s->d_n0_raw + (size_t)wbuf * s->cfg.max_blocks * s->chans.size();
+    n.n0_smooth = s->d_n0_smooth + (size_t)wbuf * s->cfg.max_blocks * s->chans.size();
+    n.state = s->d_n0_state;
+    K9_CHECK(n0_launch(n, s->s_n0) == 0, "n0 kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    K9_CUDA(cudaEventRecord(s->e_n0, s->s_n0));
+    K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_n0, 0));
+  }
   if (s->n_am) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_am, 0));
   if (s->n_lin) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_lin, 0));
   K9_CUDA(cudaEventRecord(s->e_chan1, s->s_comp));
@@ -677,6 +747,7 @@ int ka9q_stream_sync(ka9q_stream* s) {
   K9_CUDA(cudaStreamSynchronize(s->s_comp));
   K9_CUDA(cudaStreamSynchronize(s->s_am));
   K9_CUDA(cudaStreamSynchronize(s->s_lin));
+  if (s->s_n0) K9_CUDA(cudaStreamSynchronize(s->s_n0));
   K9_CUDA(cudaStreamSynchronize(s->s_out));
   return 0;
 }
@@ -759,7 +830,9 @@ static void release_resources(ka9q_stream* s) {
                   (void**)&s->d_spec, (void**)&s->d_tmp0, (void**)&s->d_tmp1, (void**)&s->d_energy, (void**)&s->d_tw2048,
                   (void**)&s->d_params, (void**)&s->d_state, (void**)&s->d_resp, (void**)&s->d_audio_resp,
                   (void**)&s->d_audio_hist, (void**)&s->d_pcm, (void**)&s->d_status, (void**)&s->d_filt,
-                  (void**)&s->d_windows, (void**)&s->d_work_fm, (void**)&s->d_work_am, (void**)&s->d_work_lin};
+                  (void**)&s->d_windows, (void**)&s->d_work_fm, (void**)&s->d_work_am, (void**)&s->d_work_lin,
+                  (void**)&s->d_n0_chan, (void**)&s->d_n0_P, (void**)&s->d_n0_T, (void**)&s->d_n0_list, (void**)&s->d_n0_raw,
+                  (void**)&s->d_n0_smooth, (void**)&s->d_n0_state, (void**)&s->d_n0_partial, (void**)&s->d_n0_blk};
   for (void** p : dev) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -769,14 +842,14 @@ static void release_resources(ka9q_stream* s) {
     if (*p) cudaFreeHost(*p);
     *p = nullptr;
   }
-  cudaStream_t* sts[] = {&s->s_in, &s->s_comp, &s->s_out, &s->s_fm, &s->s_am, &s->s_lin, &s->s_fft};
+  cudaStream_t* sts[] = {&s->s_in, &s->s_comp, &s->s_out, &s->s_fm, &s->s_am, &s->s_lin, &s->s_fft, &s->s_n0};
   for (auto st : sts) {
     if (*st) cudaStreamDestroy(*st);
     *st = nullptr;
   }
   cudaEvent_t* evs[] = {&s->e_pushed, &s->e_fft0, &s->e_fft1, &s->e_chan1, &s->e_fork, &s->e_am, &s->e_lin, &s->e_fm,
                         &s->e_comp_done[0], &s->e_comp_done[1], &s->e_fetched[0], &s->e_fetched[1], &s->e_spec_ready[0],
-                        &s->e_spec_ready[1], &s->e_spec_free[0], &s->e_spec_free[1], &s->e_t0, &s->e_t1};
+                        &s->e_spec_ready[1], &s->e_spec_free[0], &s->e_spec_free[1], &s->e_t0, &s->e_t1, &s->e_n0};
   for (auto e : evs) {
     if (*e) cudaEventDestroy(*e);
     *e = nullptr;

@@ -7,6 +7,7 @@
 #include "../../include/ka9q_b200.h"
 #include "bigfft.cuh"
 #include "chan.cuh"
+#include "n0.cuh"
 
 #include "util.cuh"
 using namespace k9;  // private header of two translation units
@@ -76,6 +77,15 @@ struct ka9q_stream {
   bool fft_pending = false;
   int fft_blocks_per_launch = 0;  // 0 = all blocks of the batch in one launch per pass (measured faster than per-block)
   bool overlap = true;  // false: the forward FFT waits for the previous batch's channel kernels (per-kernel timing)
+  // K6 noise density (n0.cu): enabled by ka9q_stream_enable_n0 before commit
+  bool n0_enabled = false;
+  cudaStream_t s_n0 = nullptr;
+  cudaEvent_t e_n0 = nullptr;
+  N0Chan* d_n0_chan = nullptr;
+  float *d_n0_P = nullptr, *d_n0_T = nullptr, *d_n0_list = nullptr, *d_n0_raw = nullptr, *d_n0_smooth = nullptr,
+        *d_n0_state = nullptr;
+  double* d_n0_partial = nullptr;
+  N0Block* d_n0_blk = nullptr;
   // NCCL (dlopen'ed)
   void* nccl_comm = nullptr;
   int nccl_rank = 0, nccl_nranks = 1;

@@ -41,7 +41,23 @@ def _plan():
     return plan
 
 
-def _worker(rank, world, port, mode, q):
+_STIM = {}
+
+
+def _stimulus(plan, nb):
+    """generated once per session (time-domain synthesis of 26 carriers), handed to the rank processes through a file"""
+    if nb not in _STIM:
+        import tempfile
+        from ka9q_sdr_b200 import synth
+        iq = synth.multi_channel(plan.samprate, nb, [c.bin for c in plan.channels], [c.mode for c in plan.channels],
+                                 plan.seed, plan.amplitude, plan.sigma)["iq"]
+        path = os.path.join(tempfile.gettempdir(), f"k9_mgpu_iq_{os.getpid()}_{nb}.npy")
+        np.save(path, iq)
+        _STIM[nb] = (iq, path)
+    return _STIM[nb]
+
+
+def _worker(rank, world, port, mode, q, iq_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import ctypes as C
     import torch.distributed as dist
@@ -49,10 +65,9 @@ def _worker(rank, world, port, mode, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         plan = _plan()
-        B, nbatch = 4, 3
+        B, nbatch = 4, 2
         nb = B * nbatch
-        iq = synth.multi_channel(plan.samprate, nb, [c.bin for c in plan.channels], [c.mode for c in plan.channels],
-                                 plan.seed, plan.amplitude, plan.sigma)["iq"]
+        iq = np.load(iq_path)
         mine = workloads.shard_contiguous(plan, rank, world)
         c = ch.Channelizer(plan.samprate, plan.L, plan.M, plan.D, device=rank, max_blocks=B)
         for s in mine:
@@ -77,7 +92,8 @@ def _worker(rank, world, port, mode, q):
                 c.push(blk.ctypes.data_as(C.c_void_p), B)
                 c.mgpu_compute(B, resident=True)
             else:
-                c.push(blk.ctypes.data_as(C.c_void_p), B)      # every rank keeps a ring; only rank 0's is transformed
+                if rank == 0 or k == 0:                        # only rank 0's ring is transformed; the other ranks push
+                    c.push(blk.ctypes.data_as(C.c_void_p), B)  # once so that their block counter starts like rank 0's
                 if rank == 0:
                     c.compute_fft_only(B)
                 c.nccl_broadcast_spectrum(B, 0)
@@ -100,14 +116,13 @@ def test_sharded_two_gpus_equal_one_gpu(mode):
     from ka9q_sdr_b200 import channelizer as ch, synth
     world = 2
     plan = _plan()
-    B, nbatch = 4, 3
+    B, nbatch = 4, 2
     nb = B * nbatch
-    iq = synth.multi_channel(plan.samprate, nb, [c.bin for c in plan.channels], [c.mode for c in plan.channels],
-                             plan.seed, plan.amplitude, plan.sigma)["iq"]
+    iq, iq_path = _stimulus(plan, nb)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q, iq_path)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]

@@ -211,3 +211,38 @@ def test_fm_squelch_every_block_compared(ref):
             assert d[b].max() <= PCM_TOL, f"block {b}: {report[b]}"
     assert np.abs(got[8]).max() == 0      # shut squelch sends zeros (fm.c:155-160)
     c.close()
+
+
+def test_noise_density_n0_matches_compute_n0(ref):
+    """K6 (csrc/n0.cu) against the reference's per-channel compute_n0 (radio.c:383-425) and its smoothing into
+    demod->sig.n0 (fm.c:78-82: 0.01 per block; am.c:46-49, linear.c:123-126: 0.001), cfg3 geometry (N = 81 920): FM channels at
+    both band edges and around DC plus one AM and one USB channel. Bar: 1e-3 relative on sig.n0 from block 0 on."""
+    plan = workloads.cfg3()
+    nb = 8
+    mds = ["FM"] * 64
+    mds[10], mds[40] = "AM", "USB"
+    cfg = synth.multi_channel(plan.samprate, nb, [s.bin for s in plan.channels], mds, plan.seed, plan.amplitude, plan.sigma,
+                              deviation=plan.deviation)
+    fs, L, M, D, N = plan.samprate, plan.L, plan.M, plan.D, plan.N
+    c = ch.Channelizer(fs, L, M, D, max_blocks=4)
+    c.enable_n0()
+    for s, m in zip(plan.channels, mds):
+        c.add_channel(m, s.bin)
+    c.commit()
+    sm = []
+    raw = []
+    for k in range(nb // 4):
+        c.process(cfg["iq"][2 * k * 4 * L:2 * (k + 1) * 4 * L])
+        r, s_ = c.fetch_n0(4)
+        raw.append(r)
+        sm.append(s_)
+    raw, sm = np.concatenate(raw), np.concatenate(sm)
+    assert np.isfinite(raw).all() and (raw > 0).all()
+    for j in (0, 10, 31, 32, 40, 63):
+        k = plan.channels[j].bin
+        r = ref.chain_run(mds[j], fs, L, M, D, cfg["iq"], carrier_hz=k * fs / N, lo_cycles=-k / N, pkt_samples=4096)
+        np.testing.assert_allclose(sm[:, j], r.status["n0"][:nb], rtol=1e-3, err_msg=f"channel {j} ({mds[j]})")
+    # the estimate is the noise floor: sigma^2 per component -> 2 sigma^2 / Fs per Hz, /2 for the 0 dBFS convention
+    expect = plan.sigma ** 2 / fs
+    assert 0.7 < np.median(raw) / expect < 2.0      # (leakage of the 64 unwindowed carriers lifts the floor a little)
+    c.close()
