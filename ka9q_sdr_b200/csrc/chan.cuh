@@ -42,6 +42,25 @@ struct ChanState {
   double shift_phase;    // turns, phase of the post-detection shift oscillator at the start of the next block
 };
 
+// Coherent (pll / square) linear channels: constants of linear.c:29-65 evaluated on the host in the reference's types
+struct PllParams {
+  float samptime, blocktime;        // linear.c:29-30
+  float snrthresh;                  // linear.c:49
+  int lock_limit;                   // linear.c:50
+  float binsize;                    // linear.c:51
+  int lowlimit, highlimit;          // linear.c:55-56
+  float integrator_gain, prop_gain; // linear.c:63,65
+};
+struct PllState {
+  double2 coarse_ph, fine_ph;       // NCO phasors (struct osc, osc.h:9-17)
+  double coarse_freq, fine_freq;    // cycles per sample
+  float integrator, delta_f;        // linear.c:107-108
+  int lock_count, pll_lock;         // linear.c:110, demod->sig.pll_lock
+  int fft_samples, fft_ptr;         // linear.c:112,87
+  float snr, foffset, cphase;       // demod->sig.*
+  int pad_;
+};
+
 struct ChanStatus {      // mirrors the demod->sig.* scalars the reference demodulators publish
   float bb_power;        // fm.c:99, am.c:78, linear.c:302
   float snr;             // fm.c:102-103 (NAN for AM / non-PLL linear, linear.c:309)
@@ -84,6 +103,10 @@ struct ChanLaunch {
   float* agc_x;              // [nblocks*nwork][olen]: amplitude in; AM: (s - DC)*gain out, linear: gain out
   float2* agc_y;             // [nblocks*nwork][olen]: kept filter output (linear only)
   float* agc_pow;            // [nblocks*nwork][2]: block sums (am.c:56-58 / linear.c:256-261)
+  // coherent linear channels (work = (chan, pll slot))
+  const PllParams* pll_params;
+  PllState* pll_state;
+  float2* pll_ring;          // [npll][65536] carrier-search ring (linear.c:84-93)
 };
 
 // mixed: AM / linear kernels of the same stream run beside this one (they need the maximum shared-memory carve-out; CTAs
@@ -91,5 +114,6 @@ struct ChanLaunch {
 int launch_fm(const ChanLaunch& a, cudaStream_t st, bool mixed);
 int launch_am(const ChanLaunch& a, cudaStream_t st);
 int launch_linear(const ChanLaunch& a, cudaStream_t st);
+int launch_pll(const ChanLaunch& a, cudaStream_t st);
 
 }  // namespace k9

@@ -1296,6 +1296,10 @@ __global__ void agc_shift_advance_kernel(const ChanLaunch a) {
   }
 }
 
+}  // namespace k9
+#include "pll_kernel.cuh"
+namespace k9 {
+
 // ---------------------------------------------------------------- launchers
 
 int launch_fm(const ChanLaunch& a, cudaStream_t st, bool mixed) {

@@ -214,11 +214,12 @@ int ka9q_stream_add_channel(ka9q_stream* s, const ka9q_chan_params* p) {
   K9_CHECK(s && p, "null argument");
   K9_CHECK(!s->committed, "channels must be added before commit");
   K9_CHECK(p->demod_type >= 0 && p->demod_type <= 2, "bad demod_type");
-  K9_CHECK(!(p->flags & (KA9Q_FLAG_PLL | KA9Q_FLAG_SQUARE)),
-           "PLL / squaring carrier tracking (linear.c:129-246) is not implemented in this build");
+  K9_CHECK(!(p->flags & (KA9Q_FLAG_PLL | KA9Q_FLAG_SQUARE)) || p->demod_type == KA9Q_LINEAR_DEMOD,
+           "pll / square are options of the linear demodulator (modes.c:104-120)");
   K9_CHECK(!(p->hangtime < 0), "negative AGC hang time");
   K9_CHECK(!isnan(p->low) && !isnan(p->high), "filter edges must be set (set_filter returns -1 on NAN, filter.c:504)");
   ka9q_chan_params q = *p;
+  if (q.flags & KA9Q_FLAG_SQUARE) q.flags |= KA9Q_FLAG_PLL;  // square implies pll (modes.c:113-116)
   if (q.low > q.high) std::swap(q.low, q.high);  // radio.c:347-353
   if (isnan(q.headroom)) q.headroom = default_headroom();
   if (q.channels != 1 && q.channels != 2) q.channels = (q.demod_type == KA9Q_LINEAR_DEMOD) ? 2 : 1;
@@ -314,7 +315,8 @@ static int commit_impl(ka9q_stream* s) {
   memset(st.data(), 0, sizeof(ChanState) * K);
   std::vector<float> audio_betas;
   std::map<int, std::vector<int>> fm_groups;  // audio slot -> channels
-  std::vector<int2> w_fm, w_am, w_lin;
+  std::vector<int2> w_fm, w_am, w_lin, w_pll;
+  std::vector<PllParams> pll_params;
   long long off = 0;
   bool any_fm = false;
   float const dsamprate = (float)s->cfg.samprate / s->cfg.decimate;
@@ -360,7 +362,35 @@ static int commit_impl(ka9q_stream* s) {
         st[c].agc_gain = dB2voltage_f(100.0);  // linear.c:39
         // radio.c:313: shift * decimate / samprate, cycles per output sample
         P.shift_cycles = (p.shift == 0) ? 0.0 : (double)p.shift * s->cfg.decimate / (double)s->cfg.samprate;
-        w_lin.push_back(make_int2(c, -1));
+        if (p.flags & KA9Q_FLAG_PLL) {
+          // coherent modes: constants of linear.c:29-65 in the reference's own types and order of evaluation
+          const bool square = p.flags & KA9Q_FLAG_SQUARE;
+          PllParams Q;
+          memset(&Q, 0, sizeof(Q));
+          Q.samptime = samptime;
+          Q.blocktime = samptime * L;
+          float const snrthreshdb = 3;
+          int const fftsize = 1 << 16;
+          float const damping = M_SQRT1_2;
+          float const lock_time = 1;
+          Q.snrthresh = powf(10, snrthreshdb / 10);
+          Q.lock_limit = (int)round(lock_time / samptime);
+          Q.binsize = 1. / (fftsize * samptime);
+          float const searchhigh = 300, searchlow = -300;
+          Q.lowlimit = (int)round((square ? 2 : 1) * searchlow / Q.binsize);
+          Q.highlimit = (int)round((square ? 2 : 1) * searchhigh / Q.binsize);
+          float const loop_bw = 1;  // linear.c:26
+          float const vcogain = 2 * M_PI, pdgain = 1;
+          float const natfreq = loop_bw * 2 * M_PI;
+          float const tau1 = vcogain * pdgain / (natfreq * natfreq);
+          Q.integrator_gain = 1 / tau1;
+          float const tau2 = 2 * damping / natfreq;
+          Q.prop_gain = tau2 / tau1;
+          w_pll.push_back(make_int2(c, (int)pll_params.size()));
+          pll_params.push_back(Q);
+        } else {
+          w_lin.push_back(make_int2(c, -1));
+        }
       }
     }
   }
@@ -372,13 +402,29 @@ static int commit_impl(ka9q_stream* s) {
   s->n_fm = (int)w_fm.size();
   s->n_am = (int)w_am.size();
   s->n_lin = (int)w_lin.size();
+  s->n_pll = (int)w_pll.size();
   auto upload_work = [&](const std::vector<int2>& w, int2** d) -> int {
     if (w.empty()) return 0;
     K9_CUDA(cudaMalloc(d, sizeof(int2) * w.size()));
     K9_CUDA(cudaMemcpy(*d, w.data(), sizeof(int2) * w.size(), cudaMemcpyHostToDevice));
     return 0;
   };
-  if (upload_work(w_fm, &s->d_work_fm) || upload_work(w_am, &s->d_work_am) || upload_work(w_lin, &s->d_work_lin)) return -1;
+  if (upload_work(w_fm, &s->d_work_fm) || upload_work(w_am, &s->d_work_am) || upload_work(w_lin, &s->d_work_lin) ||
+      upload_work(w_pll, &s->d_work_pll))
+    return -1;
+  if (s->n_pll) {
+    K9_CUDA(cudaStreamCreateWithFlags(&s->s_pll, cudaStreamNonBlocking));
+    K9_CUDA(cudaEventCreateWithFlags(&s->e_pll, cudaEventDisableTiming));
+    K9_CUDA(cudaMalloc(&s->d_pll_params, sizeof(PllParams) * s->n_pll));
+    K9_CUDA(cudaMemcpy(s->d_pll_params, pll_params.data(), sizeof(PllParams) * s->n_pll, cudaMemcpyHostToDevice));
+    std::vector<PllState> ps(s->n_pll);
+    memset(ps.data(), 0, sizeof(PllState) * s->n_pll);  // sig.snr = 0 (linear.c:75), integrator, delta_f, lock_count = 0
+    for (auto& x : ps) x.coarse_ph = x.fine_ph = make_double2(1.0, 0.0);  // linear.c:99,104
+    K9_CUDA(cudaMalloc(&s->d_pll_state, sizeof(PllState) * s->n_pll));
+    K9_CUDA(cudaMemcpy(s->d_pll_state, ps.data(), sizeof(PllState) * s->n_pll, cudaMemcpyHostToDevice));
+    K9_CUDA(cudaMalloc(&s->d_pll_ring, sizeof(float2) * (size_t)s->n_pll * 65536));
+    K9_CUDA(cudaMemset(s->d_pll_ring, 0, sizeof(float2) * (size_t)s->n_pll * 65536));
+  }
   K9_CUDA(cudaMemcpy(s->d_params, s->h_params.data(), sizeof(ChanParams) * K, cudaMemcpyHostToDevice));
   K9_CUDA(cudaMemcpy(s->d_state, st.data(), sizeof(ChanState) * K, cudaMemcpyHostToDevice));
   {
@@ -463,7 +509,7 @@ long long ka9q_stream_blocks_done(const ka9q_stream* s) { return s ? s->block0 :
 int ka9q_stream_fft_size(const ka9q_stream* s) { return s ? s->N : -1; }
 int ka9q_stream_launches_per_call(const ka9q_stream* s) {
   if (!s) return -1;
-  return s->fwd.npass + (s->n_fm ? 1 : 0) + (s->n_am ? 1 : 0) + (s->n_lin ? 1 : 0);
+  return s->fwd.npass + (s->n_fm ? 1 : 0) + (s->n_am ? 1 : 0) + (s->n_lin ? 1 : 0) + (s->n_pll ? 1 : 0);
 }
 
 int ka9q_stream_push(ka9q_stream* s, const void* iq, int nblocks) {
@@ -619,11 +665,24 @@ int issue_channels(ka9q_stream* s, int nblocks) {
     }
     K9_CUDA(cudaEventRecord(s->e_lin, s->s_lin));
   }
+  if (s->n_pll) {
+    K9_CUDA(cudaStreamWaitEvent(s->s_pll, s->e_fork, 0));
+    a.work = s->d_work_pll;
+    a.nwork = s->n_pll;
+    a.pll_params = s->d_pll_params;
+    a.pll_state = s->d_pll_state;
+    a.pll_ring = s->d_pll_ring;
+    {
+      TimedRegion tr(s, TC_LIN, s->s_pll);
+      K9_CHECK(launch_pll(a, s->s_pll) == 0, "pll kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    K9_CUDA(cudaEventRecord(s->e_pll, s->s_pll));
+  }
   if (s->n_fm) {
     a.work = s->d_work_fm;
     a.nwork = s->n_fm;
     TimedRegion tr(s, TC_FM, s->s_comp);
-    K9_CHECK(launch_fm(a, s->s_comp, s->n_am + s->n_lin > 0) == 0, "fm kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    K9_CHECK(launch_fm(a, s->s_comp, s->n_am + s->n_lin + s->n_pll > 0) == 0, "fm kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (s->n0_enabled) {
     // K6 beside the channel kernels: reads the same spectrum buffer, writes the n0 rows of this batch
@@ -652,6 +711,7 @@ int issue_channels(ka9q_stream* s, int nblocks) {
   }
   if (s->n_am) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_am, 0));
   if (s->n_lin) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_lin, 0));
+  if (s->n_pll) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_pll, 0));
   K9_CUDA(cudaEventRecord(s->e_chan1, s->s_comp));
   K9_CUDA(cudaEventRecord(s->e_spec_free[p], s->s_comp));
   s->spec_rd ^= 1;
@@ -748,6 +808,7 @@ int ka9q_stream_sync(ka9q_stream* s) {
   K9_CUDA(cudaStreamSynchronize(s->s_am));
   K9_CUDA(cudaStreamSynchronize(s->s_lin));
   if (s->s_n0) K9_CUDA(cudaStreamSynchronize(s->s_n0));
+  if (s->s_pll) K9_CUDA(cudaStreamSynchronize(s->s_pll));
   K9_CUDA(cudaStreamSynchronize(s->s_out));
   return 0;
 }
@@ -831,6 +892,7 @@ static void release_resources(ka9q_stream* s) {
                   (void**)&s->d_params, (void**)&s->d_state, (void**)&s->d_resp, (void**)&s->d_audio_resp,
                   (void**)&s->d_audio_hist, (void**)&s->d_pcm, (void**)&s->d_status, (void**)&s->d_filt,
                   (void**)&s->d_windows, (void**)&s->d_work_fm, (void**)&s->d_work_am, (void**)&s->d_work_lin,
+                  (void**)&s->d_work_pll, (void**)&s->d_pll_params, (void**)&s->d_pll_state, (void**)&s->d_pll_ring,
                   (void**)&s->d_n0_chan, (void**)&s->d_n0_P, (void**)&s->d_n0_T, (void**)&s->d_n0_list, (void**)&s->d_n0_raw,
                   (void**)&s->d_n0_smooth, (void**)&s->d_n0_state, (void**)&s->d_n0_partial, (void**)&s->d_n0_blk};
   for (void** p : dev) {
@@ -842,14 +904,14 @@ static void release_resources(ka9q_stream* s) {
     if (*p) cudaFreeHost(*p);
     *p = nullptr;
   }
-  cudaStream_t* sts[] = {&s->s_in, &s->s_comp, &s->s_out, &s->s_fm, &s->s_am, &s->s_lin, &s->s_fft, &s->s_n0};
+  cudaStream_t* sts[] = {&s->s_in, &s->s_comp, &s->s_out, &s->s_fm, &s->s_am, &s->s_lin, &s->s_fft, &s->s_n0, &s->s_pll};
   for (auto st : sts) {
     if (*st) cudaStreamDestroy(*st);
     *st = nullptr;
   }
   cudaEvent_t* evs[] = {&s->e_pushed, &s->e_fft0, &s->e_fft1, &s->e_chan1, &s->e_fork, &s->e_am, &s->e_lin, &s->e_fm,
                         &s->e_comp_done[0], &s->e_comp_done[1], &s->e_fetched[0], &s->e_fetched[1], &s->e_spec_ready[0],
-                        &s->e_spec_ready[1], &s->e_spec_free[0], &s->e_spec_free[1], &s->e_t0, &s->e_t1, &s->e_n0};
+                        &s->e_spec_ready[1], &s->e_spec_free[0], &s->e_spec_free[1], &s->e_t0, &s->e_t1, &s->e_n0, &s->e_pll};
   for (auto e : evs) {
     if (*e) cudaEventDestroy(*e);
     *e = nullptr;

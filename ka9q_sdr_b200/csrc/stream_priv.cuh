@@ -58,8 +58,13 @@ struct ka9q_stream {
   float2* d_filt = nullptr;
   float* d_windows = nullptr;
   std::vector<float> betas;  // distinct Kaiser betas -> window table rows
-  int2 *d_work_fm = nullptr, *d_work_am = nullptr, *d_work_lin = nullptr;
-  int n_fm = 0, n_am = 0, n_lin = 0;
+  int2 *d_work_fm = nullptr, *d_work_am = nullptr, *d_work_lin = nullptr, *d_work_pll = nullptr;
+  int n_fm = 0, n_am = 0, n_lin = 0, n_pll = 0;
+  PllParams* d_pll_params = nullptr;
+  PllState* d_pll_state = nullptr;
+  float2* d_pll_ring = nullptr;
+  cudaStream_t s_pll = nullptr;
+  cudaEvent_t e_pll = nullptr;
   long long pcm_stride = 0;
   // pinned staging
   void* h_iq = nullptr;

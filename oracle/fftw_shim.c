@@ -155,6 +155,9 @@ void *fftwf_malloc(size_t n) {
   void *p = NULL;
   if (posix_memalign(&p, 64, n ? n : 64) != 0)
     return NULL;
+  /* zero-filled: linear.c:90-91 transforms its 64K-sample carrier-search buffer before it has been filled once
+     (fft_samples > fftsize/2), i.e. it reads memory FFTW's allocator never initialised; zeros make the oracle deterministic */
+  memset(p, 0, n ? n : 64);
   return p;
 }
 fftwf_complex *fftwf_alloc_complex(size_t n) { return fftwf_malloc(n * 2 * sizeof(float)); }

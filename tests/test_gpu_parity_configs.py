@@ -246,3 +246,35 @@ def test_noise_density_n0_matches_compute_n0(ref):
     expect = plan.sigma ** 2 / fs
     assert 0.7 < np.median(raw) / expect < 2.0      # (leakage of the 64 unwindowed carriers lifts the floor a little)
     c.close()
+
+
+@pytest.mark.parametrize("mode", ["CAM", "DSB", "AME", "CISB"])
+def test_coherent_pll_modes_against_reference(ref, mode):
+    """The pll / square rows of modes.txt (linear.c:129-246): FFT acquisition of a carrier 37.3 Hz off the channel centre
+    (found after 35 blocks, when more than half of the 65536-sample search ring is new), second-order loop pull-in, lock
+    detector with hysteresis, then the ordinary linear demodulator on the de-rotated samples. 120 blocks = 2.4 s."""
+    fs = 192000
+    D, L, M, N = synth.geometry(fs)
+    nb = 120
+    rng = np.random.default_rng(5)
+    n = nb * L
+    k, off = 1024, 37.3
+    t = np.arange(n) / fs
+    x = 0.1 * (1 + 0.5 * np.sin(2 * np.pi * 1000 * t)) * np.exp(2j * np.pi * (k * fs / N + off) * t) + synth.awgn(rng, n, 0.005)
+    iq = synth._quantize(x)
+    c = ch.Channelizer(fs, L, M, D, max_blocks=8)
+    c.add_channel(mode, k)
+    c.commit()
+    pcm, st = c.run(iq)
+    r = ref.chain_run(mode, fs, L, M, D, iq, carrier_hz=k * fs / N, lo_cycles=-k / N)
+    rs = r.status[:nb]
+    # loop state per block: lock flag (carried in squelch_open), carrier phase, loop SNR, smoothed frequency offset
+    assert np.array_equal(st["squelch_open"][:, 0], rs["pll_lock"]), "pll_lock trajectory"
+    np.testing.assert_allclose(st["reserved"][:, 0, 0], rs["cphase"], atol=2e-3)
+    np.testing.assert_allclose(st["foffset"][:, 0], rs["foffset"], atol=2e-3, rtol=1e-3)
+    np.testing.assert_allclose(st["snr"][1:, 0], rs["snr"][1:], rtol=2e-2, atol=1e-2)
+    np.testing.assert_allclose(st["agc_gain"][5:, 0], rs["agc_gain"][5:], rtol=2e-4)
+    check_pcm(mode, c.channel_pcm(pcm, 0), r.pcm, L // D)
+    if mode != "CISB":
+        assert rs["pll_lock"][-1] == 1          # the loop did lock on this stimulus
+    c.close()
