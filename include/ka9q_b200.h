@@ -317,6 +317,37 @@ int ka9q_fft_plan_describe(int n, int *sizes);
  * `stages` x (15-tap half-band /2), highest rate first, separately per plane; state16 holds stages x hb15_state. */
 int ka9q_hb15_cascade(int device, int stages, struct hb15_state *states, const float *in, int n_in, float *out);
 
+/* Front-end decimator service: the sample path of the reference's `hackrf` daemon on the device —
+ * rx_callback (hackrf.c:129-196: int8 ingest, DC removal, I/Q gain and phase correction, estimates advanced once per USB
+ * transfer) and process (hackrf.c:198-345: Fs/4 rotation, cascade of 15-tap half-band decimators on both planes,
+ * x 0.5^stages, (short)round(32767 s)). */
+typedef struct ka9q_frontend ka9q_frontend;
+typedef struct ka9q_frontend_config {
+  int device;
+  int out_samprate;      /* Out_samprate (hackrf.c:62); the A/D runs at decimate * out_samprate (hackrf.c:463) */
+  int decimate;          /* Decimate: a power of two, 2..64 (hackrf.c:63,464) */
+  int offset;            /* Offset: 1 = tuner set high by Fs/4, undone by a rotation per sample (hackrf.c:68,271-291) */
+  int callback_samples;  /* complex samples per USB transfer = per update of the estimates (hackrf.c:132,182) */
+  float dc_alpha;        /* DC_alpha (hackrf.c:74: 1e-7) */
+  float power_alpha;     /* Power_alpha (hackrf.c:75: 1.0) */
+} ka9q_frontend_config;
+typedef struct ka9q_frontend_status {  /* HackCD.* (hackrf.c:36-58) */
+  float dc_i, dc_q, imbalance, sinphi, in_power;
+  long long clips, samples;
+} ka9q_frontend_status;
+int ka9q_frontend_create(ka9q_frontend **out, const ka9q_frontend_config *cfg);
+int ka9q_frontend_destroy(ka9q_frontend *f);
+/* iq8: HOST int8 I/Q, nsamples complex samples (a whole number of callback blocks); out: HOST int16 I/Q, nsamples/decimate */
+int ka9q_frontend_process(ka9q_frontend *f, const void *iq8, long long nsamples, int16_t *out);
+/* same, the decimated stream goes device-to-device into the channelizer's ring (as ka9q_stream_push would from the host) */
+int ka9q_frontend_process_to_stream(ka9q_frontend *f, const void *iq8, long long nsamples, ka9q_stream *s);
+/* re-run the device work on the batch left resident by the last process call (benchmarks); ms = device time */
+int ka9q_frontend_rerun_resident(ka9q_frontend *f, long long nsamples, float *ms);
+int ka9q_frontend_set_estimates(ka9q_frontend *f, float dc_i, float dc_q, float imbalance, float sinphi);
+int ka9q_frontend_get_status(ka9q_frontend *f, ka9q_frontend_status *out);
+/* append nsamples complex samples that already live in DEVICE memory (the stream's iq_format) to the stream's ring */
+int ka9q_stream_push_device(ka9q_stream *s, const void *d_iq, long long nsamples);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Wire-format glue either side of the path (host C, no GPU). What `radio` does between its sockets and
  * the DSP: I/Q datagram -> sample stream with the reference's sequence / timestamp repair, and PCM rows -> RTP packets.

@@ -39,6 +39,18 @@ class StreamConfig(C.Structure):
     ]
 
 
+class FrontendConfig(C.Structure):
+    """struct ka9q_frontend_config"""
+    _fields_ = [("device", C.c_int), ("out_samprate", C.c_int), ("decimate", C.c_int), ("offset", C.c_int),
+                ("callback_samples", C.c_int), ("dc_alpha", C.c_float), ("power_alpha", C.c_float)]
+
+
+class FrontendStatus(C.Structure):
+    """struct ka9q_frontend_status"""
+    _fields_ = [("dc_i", C.c_float), ("dc_q", C.c_float), ("imbalance", C.c_float), ("sinphi", C.c_float),
+                ("in_power", C.c_float), ("clips", C.c_longlong), ("samples", C.c_longlong)]
+
+
 class Hb15State(C.Structure):
     """struct hb15_state (reference decimate.h:4-9)"""
     _fields_ = [("coeffs", C.c_float * 4), ("even_samples", C.c_float * 4), ("odd_samples", C.c_float * 4),
@@ -66,7 +78,9 @@ EXPORTED = [
     "ka9q_rtp_process", "ka9q_pcm_packetise", "ka9q_stream_wait_fetched", "ka9q_status_encode_signals",
     "ka9q_stream_needed_bins", "ka9q_stream_mgpu_export", "ka9q_stream_mgpu_setup", "ka9q_stream_mgpu_input_range",
     "ka9q_stream_push_at", "ka9q_stream_mgpu_compute", "ka9q_stream_mgpu_error", "ka9q_stream_blocks_done",
-    "ka9q_stream_enable_n0", "ka9q_stream_fetch_n0",
+    "ka9q_stream_enable_n0", "ka9q_stream_fetch_n0", "ka9q_frontend_create", "ka9q_frontend_destroy",
+    "ka9q_frontend_process", "ka9q_frontend_process_to_stream", "ka9q_frontend_rerun_resident",
+    "ka9q_frontend_set_estimates", "ka9q_frontend_get_status", "ka9q_stream_push_device",
 ]
 
 
@@ -129,6 +143,14 @@ def lib():
     L.ka9q_stream_push_at.argtypes = [vp, vp, cll, cll]
     L.ka9q_stream_mgpu_compute.argtypes = [vp, ci, ci]
     L.ka9q_stream_mgpu_error.argtypes = [vp]
+    L.ka9q_frontend_create.argtypes = [C.POINTER(vp), C.POINTER(FrontendConfig)]
+    L.ka9q_frontend_destroy.argtypes = [vp]
+    L.ka9q_frontend_process.argtypes = [vp, vp, cll, vp]
+    L.ka9q_frontend_process_to_stream.argtypes = [vp, vp, cll, vp]
+    L.ka9q_frontend_rerun_resident.argtypes = [vp, cll, C.POINTER(cf)]
+    L.ka9q_frontend_set_estimates.argtypes = [vp, cf, cf, cf, cf]
+    L.ka9q_frontend_get_status.argtypes = [vp, C.POINTER(FrontendStatus)]
+    L.ka9q_stream_push_device.argtypes = [vp, vp, cll]
     L.ka9q_stream_enable_n0.argtypes = [vp, ci]
     L.ka9q_stream_fetch_n0.argtypes = [vp, ci, vp, vp]
     L.ka9q_stream_blocks_done.argtypes = [vp]

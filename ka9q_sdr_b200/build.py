@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libka9q_b200.so")
 OBJDIR = os.path.join(HERE, "build")
 
-CU_SOURCES = ["bigfft.cu", "chan_kernels.cu", "design.cu", "stream.cu", "mgpu.cu", "n0.cu", "dropin.cu", "decimate.cu"]
+CU_SOURCES = ["bigfft.cu", "chan_kernels.cu", "design.cu", "stream.cu", "mgpu.cu", "n0.cu", "dropin.cu", "decimate.cu", "frontend.cu"]
 C_SOURCES = ["osc_host.c", "rtp_glue.c"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default", "--threads", "2"]

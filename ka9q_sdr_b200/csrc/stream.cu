@@ -538,6 +538,26 @@ int ka9q_stream_push(ka9q_stream* s, const void* iq, int nblocks) {
   return 0;
 }
 
+// Device-resident producer (the front-end service): nsamples complex samples in device memory, any count.
+int ka9q_stream_push_device(ka9q_stream* s, const void* d_iq, long long nsamples) {
+  K9_CHECK(s && s->committed && d_iq && nsamples > 0, "bad argument");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  K9_CHECK(s->pushed + nsamples - s->block0 * (long long)s->cfg.L <= 2LL * s->cfg.max_blocks * s->cfg.L,
+           "push would overwrite samples that have not been computed yet");
+  K9_CUDA(cudaStreamWaitEvent(s->s_in, s->e_comp_done[s->comp_parity], 0));
+  long long pos = (s->pushed + (s->cfg.M - 1)) % s->ring_cap, done = 0;
+  while (done < nsamples) {
+    const long long chunk = std::min(nsamples - done, s->ring_cap - pos);
+    K9_CUDA(cudaMemcpyAsync((char*)s->d_ring + pos * s->bytes_per_samp, (const char*)d_iq + done * s->bytes_per_samp,
+                            (size_t)chunk * s->bytes_per_samp, cudaMemcpyDeviceToDevice, s->s_in));
+    done += chunk;
+    pos = (pos + chunk) % s->ring_cap;
+  }
+  s->pushed += nsamples;
+  K9_CUDA(cudaEventRecord(s->e_pushed, s->s_in));
+  return 0;
+}
+
 static void fill_launch(ka9q_stream* s, ChanLaunch& a, int nblocks) {
   memset(&a, 0, sizeof(a));
   a.spec = s->d_spec;

@@ -215,22 +215,26 @@ def test_fm_squelch_every_block_compared(ref):
 
 def test_noise_density_n0_matches_compute_n0(ref):
     """K6 (csrc/n0.cu) against the reference's per-channel compute_n0 (radio.c:383-425) and its smoothing into
-    demod->sig.n0 (fm.c:78-82: 0.01 per block; am.c:46-49, linear.c:123-126: 0.001), cfg3 geometry (N = 81 920): FM channels at
-    both band edges and around DC plus one AM and one USB channel. Bar: 1e-3 relative on sig.n0 from block 0 on."""
-    plan = workloads.cfg3()
-    nb = 8
-    mds = ["FM"] * 64
-    mds[10], mds[40] = "AM", "USB"
-    cfg = synth.multi_channel(plan.samprate, nb, [s.bin for s in plan.channels], mds, plan.seed, plan.amplitude, plan.sigma,
-                              deviation=plan.deviation)
-    fs, L, M, D, N = plan.samprate, plan.L, plan.M, plan.D, plan.N
+    demod->sig.n0 (fm.c:78-82: 0.01 per block; am.c:46-49, linear.c:123-126: 0.001). Bar: 1e-3 relative on sig.n0, every block.
+
+    Run at the reference's own rate, 192 kS/s (N = 8192), because compute_n0 is only well defined there: it forms the bin
+    frequency as (float)(n * samprate) / N with an int product (radio.c:407-409), which overflows once n * samprate reaches
+    2^31 - at 1.92 MS/s that is every bin above n = 1118, and about 30 % of all bins then pass the passband test by accident
+    and are skipped (measured: the reference lands within +-0.9 % of K6 there, block by block, not closer). K6 forms the
+    product in 64 bits, i.e. what the comment above the function describes. Carriers are kept at amplitude 0.01 so that the
+    reference's float accumulation of the power spectrum (radio.c:416) stays accurate."""
+    fs = 192000
+    D, L, M, N = synth.geometry(fs)
+    nb = 12
+    bins = [-3500, -2400, -1300, -200, 900, 2000, 3100]
+    mds = ["FM", "AM", "USB", "FM", "LSB", "FM", "IQ"]
+    cfg = synth.multi_channel(fs, nb, bins, mds, 21, 0.01, 0.004)
     c = ch.Channelizer(fs, L, M, D, max_blocks=4)
     c.enable_n0()
-    for s, m in zip(plan.channels, mds):
-        c.add_channel(m, s.bin)
+    for k, m in zip(bins, mds):
+        c.add_channel(m, k)
     c.commit()
-    sm = []
-    raw = []
+    sm, raw = [], []
     for k in range(nb // 4):
         c.process(cfg["iq"][2 * k * 4 * L:2 * (k + 1) * 4 * L])
         r, s_ = c.fetch_n0(4)
@@ -238,13 +242,16 @@ def test_noise_density_n0_matches_compute_n0(ref):
         sm.append(s_)
     raw, sm = np.concatenate(raw), np.concatenate(sm)
     assert np.isfinite(raw).all() and (raw > 0).all()
-    for j in (0, 10, 31, 32, 40, 63):
-        k = plan.channels[j].bin
-        r = ref.chain_run(mds[j], fs, L, M, D, cfg["iq"], carrier_hz=k * fs / N, lo_cycles=-k / N, pkt_samples=4096)
-        np.testing.assert_allclose(sm[:, j], r.status["n0"][:nb], rtol=1e-3, err_msg=f"channel {j} ({mds[j]})")
-    # the estimate is the noise floor: sigma^2 per component -> 2 sigma^2 / Fs per Hz, /2 for the 0 dBFS convention
-    expect = plan.sigma ** 2 / fs
-    assert 0.7 < np.median(raw) / expect < 2.0      # (leakage of the 64 unwindowed carriers lifts the floor a little)
+    worst = 0.0
+    for j, (k, m) in enumerate(zip(bins, mds)):
+        r = ref.chain_run(m, fs, L, M, D, cfg["iq"], carrier_hz=k * fs / N, lo_cycles=-k / N)
+        want = r.status["n0"][:nb]
+        worst = max(worst, float(np.abs(sm[:, j] / want - 1).max()))
+        np.testing.assert_allclose(sm[:, j], want, rtol=1e-3, err_msg=f"channel {j} ({m} @ bin {k})")
+    print(f"n0: worst relative difference of sig.n0 over {len(bins)} channels x {nb} blocks = {worst:.2e}")
+    # the estimate is the noise floor: 2 sigma^2 per complex sample over Fs, halved for the 0 dBFS convention (radio.c:424)
+    expect = 0.004 ** 2 / fs
+    assert 0.7 < np.median(raw) / expect < 1.5
     c.close()
 
 
@@ -272,7 +279,9 @@ def test_coherent_pll_modes_against_reference(ref, mode):
     assert np.array_equal(st["squelch_open"][:, 0], rs["pll_lock"]), "pll_lock trajectory"
     np.testing.assert_allclose(st["reserved"][:, 0, 0], rs["cphase"], atol=2e-3)
     np.testing.assert_allclose(st["foffset"][:, 0], rs["foffset"], atol=2e-3, rtol=1e-3)
-    np.testing.assert_allclose(st["snr"][1:, 0], rs["snr"][1:], rtol=2e-2, atol=1e-2)
+    # (the harness captures a row when the demodulator sends its PCM, linear.c:291-299, i.e. BEFORE linear.c:304-309
+    # computes the block's loop SNR: reference row b carries the SNR of block b-1)
+    np.testing.assert_allclose(st["snr"][:-1, 0], rs["snr"][1:], rtol=1e-2, atol=1e-3)
     np.testing.assert_allclose(st["agc_gain"][5:, 0], rs["agc_gain"][5:], rtol=2e-4)
     check_pcm(mode, c.channel_pcm(pcm, 0), r.pcm, L // D)
     if mode != "CISB":
