@@ -107,6 +107,12 @@ def lib():
     L.fftwf_plan_dft_c2r_1d.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint]
     L.fftwf_execute.argtypes = [C.c_void_p]
     L.fftwf_destroy_plan.argtypes = [C.c_void_p]
+    L.ref_frontend_create.restype = C.c_void_p
+    L.ref_frontend_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+    L.ref_frontend_destroy.argtypes = [C.c_void_p]
+    L.ref_frontend_set_estimates.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
+    L.ref_frontend_status.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_frontend_process.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
     _lib = L
     return L
 
@@ -341,3 +347,35 @@ def glue_status(demod_type: int, isb: int, noise_bw: float, if_power: float, bb_
     out = np.zeros(256, dtype=np.uint8)
     n = lib().ref_glue_status(demod_type, isb, noise_bw, if_power, bb_power, gain, pdev, foffset, snr, channels, _ptr(out))
     return out[:n].tobytes()
+
+
+# ---- front-end decimator service: oracle/frontend_ref.c, a restatement of hackrf.c's sample path around the
+# verbatim decimate.c ----
+class Frontend:
+    def __init__(self, out_samprate: int, decimate: int, offset: int, callback_samples: int, dc_alpha: float = 1e-7,
+                 power_alpha: float = 1.0):
+        self.h = lib().ref_frontend_create(out_samprate, decimate, offset, callback_samples, dc_alpha, power_alpha)
+        self.decimate = decimate
+
+    def set_estimates(self, dc_i, dc_q, imbalance, sinphi):
+        lib().ref_frontend_set_estimates(self.h, dc_i, dc_q, imbalance, sinphi)
+
+    def process(self, iq8: np.ndarray) -> np.ndarray:
+        iq8 = np.ascontiguousarray(iq8, dtype=np.int8)
+        n = iq8.size // 2
+        out = np.zeros(2 * (n // self.decimate), dtype=np.int16)
+        r = lib().ref_frontend_process(self.h, _ptr(iq8), n, _ptr(out))
+        if r < 0:
+            raise RuntimeError("ref_frontend_process failed")
+        return out
+
+    def status(self):
+        o = np.zeros(7, dtype=np.float32)
+        lib().ref_frontend_status(self.h, _ptr(o))
+        return dict(dc_i=float(o[0]), dc_q=float(o[1]), imbalance=float(o[2]), sinphi=float(o[3]), in_power=float(o[4]),
+                    clips=int(o[5]))
+
+    def close(self):
+        if self.h:
+            lib().ref_frontend_destroy(self.h)
+            self.h = None
