@@ -28,6 +28,7 @@ struct ChanParams {
   double shift_cycles;   // post-detection shift, cycles per output sample (radio.c:313)
   int audio_slot;        // FM: index of the audio (de-emphasis) response, -1 = flat
   int phase_step;        // (bin * L) mod N: per-block advance of the LO phase index
+  int resp_slot;         // row of the response table this channel reads: channels with identical filters share one row
 };
 
 struct ChanState {

@@ -574,13 +574,13 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
           if (t == 0) tma_issue_window(sh.buf, X, (int)sh.P[h].bin, &sh.tma_bar);
           mbar_wait(&sh.tma_bar, tma_phase);
           tma_phase ^= 1;
-          load_filtered16_staged(v, sh.buf, (int)sh.P[h].bin, a.resp + (long long)c * NDEC);
+          load_filtered16_staged(v, sh.buf, (int)sh.P[h].bin, a.resp + (long long)sh.P[h].resp_slot * NDEC);
         } else
 #elif FM_TMA == 2
         if (use_tma) {
           mbar_wait(&sh.tma_bar, tma_phase);
           tma_phase ^= 1;
-          load_filtered16_staged(v, sh.land, (int)sh.P[h].bin, a.resp + (long long)c * NDEC);
+          load_filtered16_staged(v, sh.land, (int)sh.P[h].bin, a.resp + (long long)sh.P[h].resp_slot * NDEC);
           __syncthreads();  // the landing buffer has been read by everybody: start the next window's copy
           if (t == 0) {
             if (h == 0 && wk.y >= 0)
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
           }
         } else
 #endif
-          load_filtered16(v, X, a.N, (int)sh.P[h].bin, a.resp + (long long)c * NDEC);
+          load_filtered16(v, X, a.N, (int)sh.P[h].bin, a.resp + (long long)sh.P[h].resp_slot * NDEC);
       } else if (job == 2) {
         if (!filtered) break;
         // Two real channels ride one complex transform, z = audA + j audB (the filter's impulse response is real),
@@ -718,11 +718,11 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
       const int bin = (int)a.params[c].bin;
       const bool isb = LINEAR && (a.params[c].flags & CH_ISB);
       if (isb) {  // CTA-uniform; the mirror-bin fold is staged through shared memory
-        stage_filtered_isb(X, a.N, bin, a.resp + (long long)c * NDEC, sh.buf);
+        stage_filtered_isb(X, a.N, bin, a.resp + (long long)a.params[c].resp_slot * NDEC, sh.buf);
         __syncthreads();
         load16(v, sh.buf);
       } else {
-        load_filtered16(v, X, a.N, bin, a.resp + (long long)c * NDEC);  // straight into the transform's registers
+        load_filtered16(v, X, a.N, bin, a.resp + (long long)a.params[c].resp_slot * NDEC);  // straight into the transform's registers
       }
       fft2048<+1>(v, sh.buf, a.tw2048, sh.tw2);
       // amplitudes (am.c:56-58, linear.c:256-261) and block power straight from the registers
@@ -935,7 +935,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 8) agc_front_kernel(const Cha
   const int jb = first >> 7, rem = first & 127;
   const int bin = (int)a.params[c].bin;
   const bool isb = LINEAR && (a.params[c].flags & CH_ISB);
-  const float2* H = a.resp + (long long)c * NDEC;
+  const float2* H = a.resp + (long long)a.params[c].resp_slot * NDEC;
   float2 v[16];
   fft2048_stage_tw2(sh.tw2, a.tw2048);
   __syncthreads();

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 2) pll_kernel(const ChanLaunc
   ChanState CS = a.state[c];
   float2* ring = a.pll_ring + (long long)slot * PLL_FFT;
   const bool isb = P.flags & CH_ISB, square = P.flags & CH_SQUARE;
-  const float2* H = a.resp + (long long)c * NDEC;
+  const float2* H = a.resp + (long long)P.resp_slot * NDEC;
   int eph = phase_index0(P.bin, a.start0, a.N);
   fft2048_stage_tw2(sh.tw2, a.tw2048);
   __syncthreads();

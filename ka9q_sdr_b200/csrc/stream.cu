@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <array>
 #include <map>
 #include <vector>
 #include "../../include/ka9q_b200.h"
@@ -69,15 +70,38 @@ static float response_gain(const ka9q_stream* s, const ka9q_chan_params& p) {
   return gain;
 }
 
+// Designs the responses of channels [first, first + count). Channels whose set_filter arguments are identical (edges,
+// gain, window) get ONE row of the response table: the design runs once per distinct filter and the channel kernels of
+// all of them read the same 16 KB (L1 / L2 resident) instead of one private copy each — at cfg5 all 8192 responses are
+// the same filter. Row c is channel c's own row; resp_slot points a follower at its group's first channel. Channels
+// outside the range keep their rows (retuning one channel after commit gives it a private row again, see set_filter).
 static int design_channels(ka9q_stream* s, int first, int count) {
-  // windows for every distinct beta
-  std::vector<DesignSpec> specs(count);
+  std::vector<DesignSpec> all(count);
   for (int i = 0; i < count; i++) {
     const ka9q_chan_params& p = s->chans[first + i];
-    normalised_edges(s, p, &specs[i].low, &specs[i].high);
-    specs[i].gain = response_gain(s, p);
-    specs[i].window = window_index(s, p.kaiser_beta);
+    normalised_edges(s, p, &all[i].low, &all[i].high);
+    all[i].gain = response_gain(s, p);
+    all[i].window = window_index(s, p.kaiser_beta);
   }
+  // group identical specs: leader[i] = index (within the range) of the first channel with the same filter
+  std::vector<int> leader(count), uniq;
+  {
+    std::map<std::array<float, 4>, int> seen;
+    for (int i = 0; i < count; i++) {
+      const std::array<float, 4> key = {all[i].low, all[i].high, all[i].gain, (float)all[i].window};
+      auto it = seen.find(key);
+      if (it == seen.end()) {
+        seen[key] = i;
+        leader[i] = i;
+        uniq.push_back(i);
+      } else {
+        leader[i] = it->second;
+      }
+    }
+  }
+  const int nu = (int)uniq.size();
+  std::vector<DesignSpec> specs(nu);
+  for (int u = 0; u < nu; u++) specs[u] = all[uniq[u]];
   const int nb = (int)s->betas.size();
   std::vector<float> win((size_t)nb * s->mdec);
   for (int i = 0; i < nb; i++) kaiser_window_host(&win[(size_t)i * s->mdec], s->mdec, s->betas[i]);
@@ -85,19 +109,25 @@ static int design_channels(ka9q_stream* s, int first, int count) {
   K9_CUDA(cudaMalloc(&s->d_windows, sizeof(float) * win.size()));
   K9_CUDA(cudaMemcpy(s->d_windows, win.data(), sizeof(float) * win.size(), cudaMemcpyHostToDevice));
   DesignSpec* d_specs = nullptr;
-  float2* d_work = nullptr;
+  float2 *d_work = nullptr, *d_out = nullptr;
   float* d_ng = nullptr;
-  K9_CUDA(cudaMalloc(&d_specs, sizeof(DesignSpec) * count));
-  K9_CUDA(cudaMalloc(&d_work, sizeof(float2) * 2 * (size_t)count * NDEC));
-  K9_CUDA(cudaMalloc(&d_ng, sizeof(float) * count));
-  K9_CUDA(cudaMemcpy(d_specs, specs.data(), sizeof(DesignSpec) * count, cudaMemcpyHostToDevice));
-  int r = design_complex_batch(&s->p2048, NDEC, s->mdec, d_specs, count, s->d_windows, s->d_resp + (size_t)first * NDEC,
-                               d_work, s->s_comp);
+  K9_CUDA(cudaMalloc(&d_specs, sizeof(DesignSpec) * nu));
+  K9_CUDA(cudaMalloc(&d_work, sizeof(float2) * 2 * (size_t)nu * NDEC));
+  K9_CUDA(cudaMalloc(&d_ng, sizeof(float) * nu));
+  // all distinct: design straight into the channels' own rows; otherwise into a scratch table and copy the rows out
+  const bool direct = nu == count;
+  if (!direct) K9_CUDA(cudaMalloc(&d_out, sizeof(float2) * (size_t)nu * NDEC));
+  float2* out = direct ? s->d_resp + (size_t)first * NDEC : d_out;
+  K9_CUDA(cudaMemcpy(d_specs, specs.data(), sizeof(DesignSpec) * nu, cudaMemcpyHostToDevice));
+  int r = design_complex_batch(&s->p2048, NDEC, s->mdec, d_specs, nu, s->d_windows, out, d_work, s->s_comp);
   // noise_gain = N * sum |H|^2, doubled for CROSS_CONJ (filter.c:472-497): computed unscaled, scaled on the host
-  if (r == 0) r = noise_gain_device(s->d_resp + (size_t)first * NDEC, NDEC, NDEC, count, 1.0f, d_ng, s->s_comp);
-  std::vector<float> ng(count);
+  if (r == 0) r = noise_gain_device(out, NDEC, NDEC, nu, 1.0f, d_ng, s->s_comp);
+  std::vector<float> ng(nu);
   if (r == 0) {
-    cudaError_t e = cudaMemcpyAsync(ng.data(), d_ng, sizeof(float) * count, cudaMemcpyDeviceToHost, s->s_comp);
+    cudaError_t e = cudaMemcpyAsync(ng.data(), d_ng, sizeof(float) * nu, cudaMemcpyDeviceToHost, s->s_comp);
+    for (int u = 0; u < nu && e == cudaSuccess && !direct; u++)
+      e = cudaMemcpyAsync(s->d_resp + (size_t)(first + uniq[u]) * NDEC, d_out + (size_t)u * NDEC, sizeof(float2) * NDEC,
+                          cudaMemcpyDeviceToDevice, s->s_comp);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->s_comp);
     if (e != cudaSuccess) {
       set_error("filter design failed: %s", cudaGetErrorString(e));
@@ -107,15 +137,20 @@ static int design_channels(ka9q_stream* s, int first, int count) {
   cudaFree(d_specs);
   cudaFree(d_work);
   cudaFree(d_ng);
+  if (d_out) cudaFree(d_out);
   if (r) {
     if (!*get_error()) set_error("filter design launch failed");
     return -1;
   }
   s->h_noise_gain.resize(s->chans.size());
+  std::vector<int> upos(count, -1);
+  for (int u = 0; u < nu; u++) upos[uniq[u]] = u;
   for (int i = 0; i < count; i++) {
     const ka9q_chan_params& p = s->chans[first + i];
     const bool cc = p.demod_type == KA9Q_LINEAR_DEMOD && (p.flags & KA9Q_FLAG_ISB);
-    s->h_noise_gain[first + i] = cc ? 2 * s->N * ng[i] : s->N * ng[i];
+    const float g = ng[upos[leader[i]]];
+    s->h_noise_gain[first + i] = cc ? 2 * s->N * g : s->N * g;
+    s->h_params[first + i].resp_slot = first + leader[i];
   }
   return 0;
 }
@@ -425,7 +460,6 @@ static int commit_impl(ka9q_stream* s) {
     K9_CUDA(cudaMalloc(&s->d_pll_ring, sizeof(float2) * (size_t)s->n_pll * 65536));
     K9_CUDA(cudaMemset(s->d_pll_ring, 0, sizeof(float2) * (size_t)s->n_pll * 65536));
   }
-  K9_CUDA(cudaMemcpy(s->d_params, s->h_params.data(), sizeof(ChanParams) * K, cudaMemcpyHostToDevice));
   K9_CUDA(cudaMemcpy(s->d_state, st.data(), sizeof(ChanState) * K, cudaMemcpyHostToDevice));
   {
     const size_t rows_am = (size_t)B * s->n_am, rows_lin = (size_t)B * s->n_lin;
@@ -449,7 +483,8 @@ static int commit_impl(ka9q_stream* s) {
   K9_CUDA(cudaHostAlloc((void**)&s->h_pcm, sizeof(int16_t) * (size_t)B * s->pcm_stride, cudaHostAllocDefault));
   K9_CUDA(cudaHostAlloc((void**)&s->h_status, sizeof(ChanStatus) * (size_t)B * K, cudaHostAllocDefault));
 
-  if (design_channels(s, 0, K)) return -1;
+  if (design_channels(s, 0, K)) return -1;  // also assigns the response rows (resp_slot)
+  K9_CUDA(cudaMemcpy(s->d_params, s->h_params.data(), sizeof(ChanParams) * K, cudaMemcpyHostToDevice));
   if (design_audio(s, audio_betas)) return -1;
   s->committed = true;
   return 0;
@@ -466,13 +501,27 @@ int ka9q_stream_set_filter(ka9q_stream* s, int chan, float low, float high, floa
   p.low = std::min(low, high);
   p.high = std::max(low, high);
   p.kaiser_beta = kaiser_beta;
-  K9_CUDA(cudaStreamSynchronize(s->s_comp));
-  if (design_channels(s, chan, 1)) return -1;
+  if (ka9q_stream_sync(s)) return -1;
+  // channels that share this channel's response row move to a row of their own first (the new group leader's)
+  {
+    int heir = -1;
+    for (int c = 0; c < (int)s->chans.size(); c++) {
+      if (c == chan || s->h_params[c].resp_slot != chan) continue;
+      if (heir < 0) {
+        heir = c;
+        K9_CUDA(cudaMemcpy(s->d_resp + (size_t)heir * NDEC, s->d_resp + (size_t)chan * NDEC, sizeof(float2) * NDEC,
+                           cudaMemcpyDeviceToDevice));
+      }
+      s->h_params[c].resp_slot = heir;
+      K9_CUDA(cudaMemcpy(s->d_params + c, &s->h_params[c], sizeof(ChanParams), cudaMemcpyHostToDevice));
+    }
+  }
+  if (design_channels(s, chan, 1)) return -1;  // into the channel's own row
   if (p.demod_type == KA9Q_FM_DEMOD) {
     float const dsamprate = (float)s->cfg.samprate / s->cfg.decimate;
     s->h_params[chan].fm_gain = (p.headroom * M_1_PI * dsamprate) / fabsf(p.low - p.high);
-    K9_CUDA(cudaMemcpy(s->d_params + chan, &s->h_params[chan], sizeof(ChanParams), cudaMemcpyHostToDevice));
   }
+  K9_CUDA(cudaMemcpy(s->d_params + chan, &s->h_params[chan], sizeof(ChanParams), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -866,7 +915,8 @@ int ka9q_stream_get_response(ka9q_stream* s, int chan, void* out2048, float* noi
   K9_CUDA(cudaSetDevice(s->cfg.device));
   if (ka9q_stream_sync(s)) return -1;  // the work streams are non-blocking: order behind everything in flight
   if (out2048)
-    K9_CUDA(cudaMemcpy(out2048, s->d_resp + (size_t)chan * NDEC, sizeof(float2) * NDEC, cudaMemcpyDeviceToHost));
+    K9_CUDA(cudaMemcpy(out2048, s->d_resp + (size_t)s->h_params[chan].resp_slot * NDEC, sizeof(float2) * NDEC,
+                       cudaMemcpyDeviceToHost));
   if (noise_gain) *noise_gain = s->h_noise_gain[chan];
   return 0;
 }
