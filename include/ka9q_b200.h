@@ -403,6 +403,30 @@ typedef int (*ka9q_emit_fn)(void *user, const void *packet, int len); /* return 
  * arguments. */
 int ka9q_pcm_packetise(ka9q_pcm_out *out, const int16_t *pcm, int frames, int channels, ka9q_emit_fn emit, void *user);
 
+/* Receive-side host plumbing (main.c:288-365 rtp_recv + the queue side of proc_samples, radio.c:51-100): a receive thread
+ * inserts datagrams into a queue sorted by RTP sequence number (main.c:347-361), an ingest thread pops it in order, repairs
+ * sequence / timestamp gaps with zeros (ka9q_ingest_datagram) and appends to a page-locked ring of whole 20 ms blocks that
+ * ka9q_stream_push reads directly. ka9q_rx_inject / ka9q_rx_drain are the same two steps without threads or sockets. */
+typedef struct ka9q_rx ka9q_rx;
+typedef struct ka9q_rx_stats {
+  long long datagrams_queued, inserted_out_of_order, samples, zero_filled, ignored, rtp_drops, rtp_dupes;
+  int pinned;
+} ka9q_rx_stats;
+ka9q_rx *ka9q_rx_create(int iq_format, long long block_samples, int ring_blocks);
+void ka9q_rx_destroy(ka9q_rx *rx);
+int ka9q_rx_inject(ka9q_rx *rx, const void *datagram, int size);
+long long ka9q_rx_drain(ka9q_rx *rx);
+int ka9q_rx_start(ka9q_rx *rx, int fd /* bound, multicast-joined UDP socket owned by the caller */);
+int ka9q_rx_stop(ka9q_rx *rx);
+const void *ka9q_rx_peek_blocks(ka9q_rx *rx, int nblocks, int wait_ms);
+int ka9q_rx_consume(ka9q_rx *rx, int nblocks);
+long long ka9q_rx_blocks_ready(ka9q_rx *rx);
+void ka9q_rx_get_stats(ka9q_rx *rx, ka9q_rx_stats *st);
+/* Egress: one block row of ka9q_stream_fetch, every channel packetised as audio.c:32-132 (ka9q_pcm_packetise) and handed to
+ * the kernel `batch` packets at a time with sendmmsg (the reference sends one packet per send(), audio.c:73,122). */
+int ka9q_pcm_send_block(int fd, ka9q_pcm_out *outs, const int16_t *pcm_row, const int *offs, const int *channels, int nchan,
+                        int frames, int batch);
+
 /* Status side: the "signals" and demodulator section of the TLV status list that `radio` multicasts
  * (radio_status.c:171-203, encodings status.c:31-96: type byte, length byte, big-endian value with leading zero bytes
  * suppressed, EOL = 0 terminates), from one ka9q_chan_status row. Fields this library does not compute (NOISE_DENSITY,

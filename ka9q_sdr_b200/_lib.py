@@ -81,6 +81,8 @@ EXPORTED = [
     "ka9q_stream_enable_n0", "ka9q_stream_fetch_n0", "ka9q_frontend_create", "ka9q_frontend_destroy",
     "ka9q_frontend_process", "ka9q_frontend_process_to_stream", "ka9q_frontend_rerun_resident",
     "ka9q_frontend_set_estimates", "ka9q_frontend_get_status", "ka9q_stream_push_device",
+    "ka9q_rx_create", "ka9q_rx_destroy", "ka9q_rx_inject", "ka9q_rx_drain", "ka9q_rx_start", "ka9q_rx_stop",
+    "ka9q_rx_peek_blocks", "ka9q_rx_consume", "ka9q_rx_blocks_ready", "ka9q_rx_get_stats", "ka9q_pcm_send_block",
 ]
 
 
@@ -151,6 +153,23 @@ def lib():
     L.ka9q_frontend_set_estimates.argtypes = [vp, cf, cf, cf, cf]
     L.ka9q_frontend_get_status.argtypes = [vp, C.POINTER(FrontendStatus)]
     L.ka9q_stream_push_device.argtypes = [vp, vp, cll]
+    L.ka9q_rx_create.argtypes = [ci, cll, ci]
+    L.ka9q_rx_create.restype = vp
+    L.ka9q_rx_destroy.argtypes = [vp]
+    L.ka9q_rx_destroy.restype = None
+    L.ka9q_rx_inject.argtypes = [vp, vp, ci]
+    L.ka9q_rx_drain.argtypes = [vp]
+    L.ka9q_rx_drain.restype = cll
+    L.ka9q_rx_start.argtypes = [vp, ci]
+    L.ka9q_rx_stop.argtypes = [vp]
+    L.ka9q_rx_peek_blocks.argtypes = [vp, ci, ci]
+    L.ka9q_rx_peek_blocks.restype = vp
+    L.ka9q_rx_consume.argtypes = [vp, ci]
+    L.ka9q_rx_blocks_ready.argtypes = [vp]
+    L.ka9q_rx_blocks_ready.restype = cll
+    L.ka9q_rx_get_stats.argtypes = [vp, vp]
+    L.ka9q_rx_get_stats.restype = None
+    L.ka9q_pcm_send_block.argtypes = [ci, vp, vp, vp, vp, ci, ci, ci]
     L.ka9q_stream_enable_n0.argtypes = [vp, ci]
     L.ka9q_stream_fetch_n0.argtypes = [vp, ci, vp, vp]
     L.ka9q_stream_blocks_done.argtypes = [vp]

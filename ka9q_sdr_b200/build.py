@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libka9q_b200.so")
 OBJDIR = os.path.join(HERE, "build")
 
 CU_SOURCES = ["bigfft.cu", "chan_kernels.cu", "design.cu", "stream.cu", "mgpu.cu", "n0.cu", "dropin.cu", "decimate.cu", "frontend.cu"]
-C_SOURCES = ["osc_host.c", "rtp_glue.c"]
+C_SOURCES = ["osc_host.c", "rtp_glue.c", "rx_host.c"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default", "--threads", "2"]
 # experiment hook: extra -D switches for kernel variants (e.g. KA9Q_B200_NVCC_EXTRA="-DFM_CTAS_PER_SM=6")
