@@ -491,6 +491,8 @@ void bigfft_plan_destroy(BigFftPlan* plan) {
   memset(plan, 0, sizeof(*plan));
 }
 
+void bigfft_set_carveout(int pct) { set_pass128_carveout(pct); }
+
 int bigfft_exec(const BigFftPlan* plan, const BigFftIn& in, float2* out, long long out_batch_stride, float2* tmp0,
                 float2* tmp1, int batch, int sign, cudaStream_t stream) {
   const int N = plan->N;

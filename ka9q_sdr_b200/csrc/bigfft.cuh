@@ -76,6 +76,9 @@ struct BigFftIn {
 // with npass >= 2 the input is NOT modified). sign: -1 forward, +1 backward (unnormalised).
 int bigfft_exec(const BigFftPlan* plan, const BigFftIn& in, float2* out, long long out_batch_stride, float2* tmp0,
                 float2* tmp1, int batch, int sign, cudaStream_t stream);
+// preferred shared-memory carve-out (percent, or cudaSharedmemCarveoutMaxShared) of the lean pass kernels on the current
+// device: set it to the channel kernels' so that the two can share SMs (see bigfft_r128.cuh)
+void bigfft_set_carveout(int pct);
 // number of kernel launches one bigfft_exec performs
 inline int bigfft_launches(const BigFftPlan* plan) { return plan->npass; }
 

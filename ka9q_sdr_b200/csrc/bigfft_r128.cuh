@@ -211,6 +211,23 @@ __global__ void __launch_bounds__(P160_THREADS, P160_MIN_CTAS) fft_pass160_last_
   }
 }
 
+// Shared-memory carve-out of the lean pass kernels. CTAs of kernels with different carve-outs cannot be resident on one
+// SM at the same time, so a forward FFT that is meant to run BESIDE the channel kernels (the FFT of batch k+1 under the
+// channel kernels of batch k; at 1024 channels per GPU the FM kernel leaves more than half of every SM free) has to ask for
+// the same carve-out they use, or it waits until they have drained (measured at 8 GPUs: no overlap at all without this).
+static void set_pass128_carveout(int pct) {
+  static int configured[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (configured[dev] == pct + 1000) return;
+  cudaFuncSetAttribute(fft_pass128_first_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(fft_pass128_first_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(fft_pass128_mid_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(fft_pass160_last_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  configured[dev] = pct + 1000;
+}
+
 // returns cudaErrorNotSupported when the generic kernels should run this pass
 static cudaError_t launch_pass128(int R1, int R2, const PassArgs& a, int batch, int sign, cudaStream_t st) {
   if (R1 == 10 && R2 == 16 && sign < 0 && a.n_cur == 160 && a.in_mode == IN_C32 && a.ncols % 16 == 0 &&

@@ -113,6 +113,8 @@ struct ChanLaunch {
 // mixed: AM / linear kernels of the same stream run beside this one (they need the maximum shared-memory carve-out; CTAs
 // of kernels with different carve-outs cannot share an SM, so the FM kernel then gives up its larger L1)
 int launch_fm(const ChanLaunch& a, cudaStream_t st, bool mixed);
+// the carve-out (percent or cudaSharedmemCarveoutMaxShared) launch_fm asks for: kernels meant to run beside it use the same
+int fm_carveout(bool mixed);
 int launch_am(const ChanLaunch& a, cudaStream_t st);
 int launch_linear(const ChanLaunch& a, cudaStream_t st);
 int launch_pll(const ChanLaunch& a, cudaStream_t st);

@@ -913,8 +913,9 @@ __global__ void __launch_bounds__(FFT2048_THREADS, AGC_G == 4 ? (LINEAR ? 2 : 3)
 //   agc_serial_kernel  one LANE per channel, 32 channels per warp in lockstep (the recurrences are select-based): tiles of
 //                      32 samples are transposed through shared memory so every global access is a 128-byte row; the
 //                      next tile is prefetched into registers while the current one is walked
-//   agc_output_kernel  (linear) one CTA per channel: gain / LO phase / shift oscillator / scaleclip, fully parallel; AM's
-//                      (s - DC) * gain -> scaleclip is cheap enough to ride the recurrence kernel's store stage
+//                      the store stage is also the output stage: AM (s - DC) * gain, linear gain x LO phase x shift
+//                      oscillator, -> scaleclip -> PCM rows (the gains never go back to memory; the linear path's kept
+//                      samples are prefetched into the store warp's registers one tile ahead)
 // Same operations in the same order per channel as the fused kernel (bit-identical PCM), which stays selectable with
 // KA9Q_B200_AGC_FUSED=1.
 
@@ -1008,6 +1009,10 @@ struct SerialShared {
   float d[4][32 * SER_TP];  // AM: carrier level DC[n] (what the AGC follows)
   float o[4][32 * SER_TP];  // AM: s - DC
   int pcm_off[32];
+  // linear: the store warp is also the output stage (gain x LO phase x shift oscillator -> scaleclip -> PCM)
+  float2 ph[32];                     // this block's LO phase per channel row (Appendix C)
+  double shift_c[32], shift_p[32];   // post-detection shift: cycles per sample, phase (turns) at the start of the block
+  int nch[32];                       // PCM channels per row
 };
 
 __device__ __forceinline__ void ld8(float (&x)[8], const float* p) {
@@ -1050,6 +1055,25 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
     if (role == 0) sh.pcm_off[lane] = P.pcm_off;
   } else if (role == 0) {
     sh.pcm_off[lane] = 0;
+  }
+  // linear output stage (store warp): per-lane channel constants, and this warp's prefetched tile of kept samples
+  int o_eph = 0, o_pstep = 0;
+  double o_shc = 0.0, o_shp0 = 0.0;
+  float2 yv[32];
+  int pb = 0, pk = 0, pT = 0;  // block / tile-in-block / index of the next tile to prefetch
+  if (LINEAR && role == 4) {
+    if (c >= 0) {
+      const ChanParams& P = a.params[c];
+      o_eph = phase_index0(P.bin, a.start0, a.N);
+      o_pstep = P.phase_step;
+      o_shc = P.shift_cycles;
+      o_shp0 = a.state[c].shift_phase;
+      sh.nch[lane] = P.channels;
+      sh.shift_c[lane] = o_shc;
+    } else {
+      sh.nch[lane] = 1;
+      sh.shift_c[lane] = 0.0;
+    }
   }
   // rows of tile (block b, tile k) in the scratch: this lane's column of row r is tile_ptr(b, k) + r*olen
   auto tile_ptr = [&](int b, int k) -> float* {
@@ -1208,10 +1232,41 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
       if (live) {
         const float* qt = sh.q[bi] + lane;
         if (LINEAR) {
-          float* g = tile_ptr(b, k);
-#pragma unroll 8
-          for (int r = 0; r < nrows; r++)
-            if (lane < cnt) g[(long long)r * olen] = qt[r * SER_TP];
+          // linear.c:280-299 + audio.c:22-28 straight from the gains just computed (same operations and order as
+          // the fused kernel): the gain rows never go back to memory and no third kernel runs
+          if (k == 0) {  // first tile of block b: the block's LO phase and shift-oscillator phase of every row
+            if (c >= 0) {
+              sh.ph[lane] = phase_from_index(a, o_eph);
+              o_eph = phase_advance(o_eph, o_pstep, a.N);
+              sh.shift_p[lane] = o_shc != 0.0 ? o_shp0 + o_shc * (double)olen * b : 0.0;
+            }
+            __syncwarp();
+          }
+          const int o = 32 * k + lane;
+          int16_t* pcm_blk = a.pcm + (long long)b * a.pcm_stride;
+#pragma unroll
+          for (int r = 0; r < 32; r++) {
+            if (r < nrows && lane < cnt) {
+              const float gn = qt[r * SER_TP];
+              const float2 y = cmul(yv[r], sh.ph[r]);      // the block's LO phase rides the gain multiply
+              float2 z = make_float2(y.x * gn, y.y * gn);  // linear.c:280
+              const double sc = sh.shift_c[r];
+              if (sc != 0.0) {  // row-uniform: post-detection shift oscillator (linear.c:283-289, osc.c:39-51)
+                double p = sh.shift_p[r] + sc * (double)o;
+                p -= floor(p);
+                double sn, cs;
+                sincospi(2.0 * p, &sn, &cs);
+                z = cmul(z, make_float2((float)cs, (float)sn));
+              }
+              int16_t* row = pcm_blk + sh.pcm_off[r];
+              if (sh.nch[r] == 1) {
+                row[o] = scaleclip(z.x);  // linear.c:291-296
+              } else {
+                row[2 * o] = scaleclip(z.x);  // I left, Q right (linear.c:299)
+                row[2 * o + 1] = scaleclip(z.y);
+              }
+            }
+          }
         } else {
           // am.c:74 + audio.c:22-28: row r is channel w0 + r
           int16_t* pcm_blk = a.pcm + (long long)b * a.pcm_stride + 32 * k + lane;
@@ -1221,6 +1276,18 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
         }
       }
     }
+    if (LINEAR && role == 4 && T + 1 >= 0 && T + 1 < ntiles && pT == T + 1) {
+      // the kept filter-output samples of the tile this warp handles NEXT step, into registers (row r = channel w0 + r)
+      const int pcnt = min(32, olen - 32 * pk);
+      const float2* g = a.agc_y + ((long long)pb * a.nwork + w0) * olen + 32 * pk + lane;
+#pragma unroll
+      for (int r = 0; r < 32; r++) yv[r] = (r < nrows && lane < pcnt) ? __ldg(g + (long long)r * olen) : make_float2(0.f, 0.f);
+      pT++;
+      if (++pk == tpb) {
+        pk = 0;
+        pb++;
+      }
+    }
     if (live && ++k == tpb) {
       k = 0;
       b++;
@@ -1228,7 +1295,7 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
     __syncthreads();
   }
   if (c >= 0) {
-    // every field is written by the warp that advanced it (the output kernel advances the shift oscillator)
+    // every field is written by the warp that advanced it (agc_shift_advance_kernel advances the shift oscillator)
     if (role == 1 && !LINEAR) a.state[c].am_dc = dc;
     if (role == 3) {
       a.state[c].agc_gain = gain;
@@ -1237,54 +1304,7 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
   }
 }
 
-// parallel output: gain / shift / quantise (linear.c:280-299, am.c:74, audio.c:22-28); one CTA per channel and block
-// (a pure stream whose rate is set by the loads in flight: one CTA per channel looping over the blocks ran at 3.3 TB/s)
-template <bool LINEAR>
-__global__ void __launch_bounds__(FFT2048_THREADS) agc_output_kernel(const ChanLaunch a) {
-  const int t = threadIdx.x;
-  const int w = blockIdx.x, b = blockIdx.y;
-  const int c = a.work[w].x;
-  const int olen = a.olen;
-  const ChanParams& P = a.params[c];
-  const long long row = (long long)b * a.nwork + w;
-  const float* __restrict__ g = a.agc_x + row * olen;
-  int16_t* __restrict__ pcm_row = a.pcm + (long long)b * a.pcm_stride + P.pcm_off;
-  if (!LINEAR) {
-    for (int o = t; o < olen; o += FFT2048_THREADS) pcm_row[o] = scaleclip(g[o]);  // am.c:74
-    return;
-  }
-  const double shift_cycles = P.shift_cycles;
-  const bool shifted = shift_cycles != 0.0;
-  const int nch = P.channels;
-  int e = phase_index0(P.bin, a.start0, a.N);
-  for (int i = 0; i < b; i++) e = phase_advance(e, P.phase_step, a.N);
-  const float2 ph = phase_from_index(a, e);
-  // the shift oscillator's phase at the start of the launch; agc_shift_advance_kernel moves it on afterwards
-  const double phase0 = shifted ? a.state[c].shift_phase + shift_cycles * (double)olen * b : 0.0;
-  const float2* __restrict__ yk = a.agc_y + row * olen;
-  for (int o = t; o < olen; o += FFT2048_THREADS) {
-    const float gn = g[o];
-    const float2 y = cmul(yk[o], ph);            // the block's LO phase rides the gain multiply
-    float2 z = make_float2(y.x * gn, y.y * gn);  // linear.c:280
-    if (shifted) {
-      // post-detection shift oscillator (linear.c:283-289, osc.c:39-51): phasor(n) = exp(j*2*pi*f*n), n counted
-      // from the first sample the oscillator was stepped on
-      double p = phase0 + shift_cycles * (double)o;
-      p -= floor(p);
-      double sn, cs;
-      sincospi(2.0 * p, &sn, &cs);
-      z = cmul(z, make_float2((float)cs, (float)sn));
-    }
-    if (nch == 1) {
-      pcm_row[o] = scaleclip(z.x);  // linear.c:291-296
-    } else {
-      pcm_row[2 * o] = scaleclip(z.x);  // I left, Q right (linear.c:299)
-      pcm_row[2 * o + 1] = scaleclip(z.y);
-    }
-  }
-}
-
-// after the output kernel: the shift oscillators have run olen * nblocks samples further
+// after the recurrence kernel: the shift oscillators have run olen * nblocks samples further
 __global__ void agc_shift_advance_kernel(const ChanLaunch a) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= a.nwork) return;
@@ -1302,6 +1322,8 @@ namespace k9 {
 
 // ---------------------------------------------------------------- launchers
 
+int fm_carveout(bool mixed) { return mixed ? (int)cudaSharedmemCarveoutMaxShared : FM_CARVEOUT_PCT; }
+
 int launch_fm(const ChanLaunch& a, cudaStream_t st, bool mixed) {
   if (a.nwork <= 0) return 0;
   // 8 CTAs x (16.8 KB + 1 KB reserved) = 143 KB: alone, ask for the 164 KB carve-out (percent of 228 KB, rounded up by
@@ -1309,7 +1331,7 @@ int launch_fm(const ChanLaunch& a, cudaStream_t st, bool mixed) {
   // 0.491 ms per launch at cfg5); beside AM / linear kernels use their (maximum) carve-out so the CTAs can share SMs.
   // (function attributes are per device: one slot per device, so several GPUs driven from one process all get set up)
   static int configured[64];
-  const int pct = mixed ? (int)cudaSharedmemCarveoutMaxShared : FM_CARVEOUT_PCT;
+  const int pct = fm_carveout(mixed);
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
@@ -1376,10 +1398,9 @@ static int launch_agc(const ChanLaunch& a, cudaStream_t st) {
   else
     agc_front_kernel<LINEAR, 0><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
   agc_serial_kernel<LINEAR><<<(a.nwork + 31) / 32, SER_THREADS, sizeof(SerialShared), st>>>(a);
-  if (LINEAR) {  // AM: the recurrence kernel wrote the PCM
-    agc_output_kernel<LINEAR><<<dim3(a.nwork, a.nblocks), FFT2048_THREADS, 0, st>>>(a);
-    agc_shift_advance_kernel<<<(a.nwork + 127) / 128, 128, 0, st>>>(a);
-  }
+  // the recurrence kernel wrote the PCM (AM: (s - DC) * gain; linear: gain x LO phase x shift oscillator); only the
+  // shift oscillators' phase is left to advance
+  if (LINEAR) agc_shift_advance_kernel<<<(a.nwork + 127) / 128, 128, 0, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 int launch_am(const ChanLaunch& a, cudaStream_t st) { return launch_agc<false>(a, st); }

@@ -195,6 +195,11 @@ int ka9q_stream_mgpu_setup(ka9q_stream* s, int transport, int rank, int nranks, 
       s->mg_need[r].push_back({0, lo + len - N});
     }
   }
+  {  // the exchange kernels run beside the channel kernels of the previous batch: same carve-out (see bigfft_r128.cuh)
+    cudaFuncSetAttribute(mgpu_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, s->carveout);
+    cudaFuncSetAttribute(mgpu_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, s->carveout);
+    cudaFuncSetAttribute(mgpu_signal_free_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, s->carveout);
+  }
   s->mg_rank = rank;
   s->mg_nranks = nranks;
   s->mg_transport = transport;

@@ -483,6 +483,9 @@ static int commit_impl(ka9q_stream* s) {
   K9_CUDA(cudaHostAlloc((void**)&s->h_pcm, sizeof(int16_t) * (size_t)B * s->pcm_stride, cudaHostAllocDefault));
   K9_CUDA(cudaHostAlloc((void**)&s->h_status, sizeof(ChanStatus) * (size_t)B * K, cudaHostAllocDefault));
 
+  // the forward FFT (and the multi-GPU exchange kernels) run beside the channel kernels: same shared-memory carve-out
+  s->carveout = fm_carveout(s->n_am + s->n_lin + s->n_pll > 0);
+  bigfft_set_carveout(s->carveout);
   if (design_channels(s, 0, K)) return -1;  // also assigns the response rows (resp_slot)
   K9_CUDA(cudaMemcpy(s->d_params, s->h_params.data(), sizeof(ChanParams) * K, cudaMemcpyHostToDevice));
   if (design_audio(s, audio_betas)) return -1;

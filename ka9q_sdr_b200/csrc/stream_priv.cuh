@@ -29,6 +29,7 @@ struct ka9q_stream {
   ka9q_stream_config cfg;
   int N = 0, olen = 0, mdec = 0;
   int bytes_per_samp = 4;
+  int carveout = 0;            // shared-memory carve-out every kernel of this stream asks for (so they can share SMs)
   bool committed = false;
   BigFftPlan fwd, p2048;
   // device
