@@ -1003,16 +1003,13 @@ __global__ void __launch_bounds__(FFT2048_THREADS, 8) agc_front_kernel(const Cha
 constexpr int SER_TP = 36;       // tile row pitch (floats): 16-byte aligned rows, 128-bit row accesses of the 32 lanes
                                  // (one row per lane, 144 bytes apart) are bank-conflict free per quarter-warp
 constexpr int SER_THREADS = 256;  // warps: 0 load, 1 dc, 2-5 div (8 samples of the tile each), 6 agc, 7 store
+constexpr int SER_THREADS_LIN = 320;  // linear: warps 1, 7, 8, 9 are the output stage (8 samples of the tile each)
 struct SerialShared {
   float x[8][32 * SER_TP];  // amplitude tiles [channel][sample], filled by cp.async three steps ahead
   float q[4][32 * SER_TP];  // headroom / x, overwritten by the result (linear: gain; AM: (s - DC) * gain)
   float d[4][32 * SER_TP];  // AM: carrier level DC[n] (what the AGC follows)
   float o[4][32 * SER_TP];  // AM: s - DC
   int pcm_off[32];
-  // linear: the store warp is also the output stage (gain x LO phase x shift oscillator -> scaleclip -> PCM)
-  float2 ph[32];                     // this block's LO phase per channel row (Appendix C)
-  double shift_c[32], shift_p[32];   // post-detection shift: cycles per sample, phase (turns) at the start of the block
-  int nch[32];                       // PCM channels per row
 };
 
 __device__ __forceinline__ void ld8(float (&x)[8], const float* p) {
@@ -1026,12 +1023,16 @@ __device__ __forceinline__ void st8(float* p, const float (&x)[8]) {
 }
 
 template <bool LINEAR>
-__global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunch a) {
+__global__ void __launch_bounds__(LINEAR ? SER_THREADS_LIN : SER_THREADS, 2) agc_serial_kernel(const ChanLaunch a) {
   extern __shared__ __align__(16) unsigned char ser_raw[];
   SerialShared& sh = *reinterpret_cast<SerialShared*>(ser_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // pipeline stage of this warp: 0 load, 1 dc, 2 div (warps 2..5, quarter `sub` of the tile each), 3 agc, 4 store
-  const int role = warp < 2 ? warp : (warp < 6 ? 2 : warp - 3);
+  // linear: the output stage is ~25 instructions per sample, far too much for one warp inside a pipeline step (measured:
+  // 3.5 us per step with one output warp, 2 us with two, against 1.2 us for the recurrence). Four output warps — the idle
+  // DC warp, the store warp and two extra warps (SER_THREADS_LIN = 320) — take eight samples of the tile each.
+  const int role = (LINEAR && (warp == 1 || warp >= 7)) ? 4 : (warp < 2 ? warp : (warp < 6 ? 2 : warp - 3));
+  const int ow = warp == 1 ? 0 : warp - 6;  // output warp 0..3 (warps 1, 7, 8, 9)
   const int sub = warp - 2;
   const int w0 = blockIdx.x * 32;
   const int nrows = min(32, a.nwork - w0);
@@ -1056,24 +1057,21 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
   } else if (role == 0) {
     sh.pcm_off[lane] = 0;
   }
-  // linear output stage (store warp): per-lane channel constants, and this warp's prefetched tile of kept samples
-  int o_eph = 0, o_pstep = 0;
-  double o_shc = 0.0, o_shp0 = 0.0;
-  float2 yv[32];
+  // linear output stage = the store warp, one lane per channel like every other stage: the channel's constants stay in the
+  // lane's registers, its kept filter-output samples of the NEXT tile are prefetched into registers (32 x float2)
+  int o_eph = 0, o_pstep = 0, o_nch = 1, o_off = 0;
+  double o_shc = 0.0, o_shp0 = 0.0, o_shp = 0.0;
+  float2 o_ph = make_float2(1.f, 0.f);
+  float2 yv[8];                // this warp's eight samples of the next tile
   int pb = 0, pk = 0, pT = 0;  // block / tile-in-block / index of the next tile to prefetch
-  if (LINEAR && role == 4) {
-    if (c >= 0) {
-      const ChanParams& P = a.params[c];
-      o_eph = phase_index0(P.bin, a.start0, a.N);
-      o_pstep = P.phase_step;
-      o_shc = P.shift_cycles;
-      o_shp0 = a.state[c].shift_phase;
-      sh.nch[lane] = P.channels;
-      sh.shift_c[lane] = o_shc;
-    } else {
-      sh.nch[lane] = 1;
-      sh.shift_c[lane] = 0.0;
-    }
+  if (LINEAR && role == 4 && c >= 0) {
+    const ChanParams& P = a.params[c];
+    o_eph = phase_index0(P.bin, a.start0, a.N);
+    o_pstep = P.phase_step;
+    o_shc = P.shift_cycles;
+    o_shp0 = a.state[c].shift_phase;
+    o_nch = P.channels;
+    o_off = P.pcm_off;
   }
   // rows of tile (block b, tile k) in the scratch: this lane's column of row r is tile_ptr(b, k) + r*olen
   auto tile_ptr = [&](int b, int k) -> float* {
@@ -1232,38 +1230,70 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
       if (live) {
         const float* qt = sh.q[bi] + lane;
         if (LINEAR) {
-          // linear.c:280-299 + audio.c:22-28 straight from the gains just computed (same operations and order as
-          // the fused kernel): the gain rows never go back to memory and no third kernel runs
-          if (k == 0) {  // first tile of block b: the block's LO phase and shift-oscillator phase of every row
-            if (c >= 0) {
-              sh.ph[lane] = phase_from_index(a, o_eph);
-              o_eph = phase_advance(o_eph, o_pstep, a.N);
-              sh.shift_p[lane] = o_shc != 0.0 ? o_shp0 + o_shc * (double)olen * b : 0.0;
-            }
-            __syncwarp();
+          // linear.c:280-299 + audio.c:22-28 straight from the gains just computed (same operations and order as the
+          // fused kernel): the gain rows never go back to memory and no third kernel runs. Lane = channel.
+          if (k == 0) {  // first tile of block b: the block's LO phase and shift-oscillator phase
+            o_ph = phase_from_index(a, o_eph);
+            o_eph = phase_advance(o_eph, o_pstep, a.N);
+            o_shp = o_shc != 0.0 ? o_shp0 + o_shc * (double)olen * b : 0.0;
           }
-          const int o = 32 * k + lane;
-          int16_t* pcm_blk = a.pcm + (long long)b * a.pcm_stride;
+          if (c >= 0) {
+            const float* qr = sh.q[bi] + lane * SER_TP;
+            int16_t* row = a.pcm + (long long)b * a.pcm_stride + o_off + (long long)o_nch * 32 * k;
+            {
+              const int h0 = 0;
+              const int i0 = 8 * ow;  // first sample of this warp's group inside the tile
+              if (i0 < cnt) {  // warp-uniform
+                float gn[8];
+                ld8(gn, qr + i0);
+                int16_t out[16];
 #pragma unroll
-          for (int r = 0; r < 32; r++) {
-            if (r < nrows && lane < cnt) {
-              const float gn = qt[r * SER_TP];
-              const float2 y = cmul(yv[r], sh.ph[r]);      // the block's LO phase rides the gain multiply
-              float2 z = make_float2(y.x * gn, y.y * gn);  // linear.c:280
-              const double sc = sh.shift_c[r];
-              if (sc != 0.0) {  // row-uniform: post-detection shift oscillator (linear.c:283-289, osc.c:39-51)
-                double p = sh.shift_p[r] + sc * (double)o;
-                p -= floor(p);
-                double sn, cs;
-                sincospi(2.0 * p, &sn, &cs);
-                z = cmul(z, make_float2((float)cs, (float)sn));
-              }
-              int16_t* row = pcm_blk + sh.pcm_off[r];
-              if (sh.nch[r] == 1) {
-                row[o] = scaleclip(z.x);  // linear.c:291-296
-              } else {
-                row[2 * o] = scaleclip(z.x);  // I left, Q right (linear.c:299)
-                row[2 * o + 1] = scaleclip(z.y);
+                for (int i = 0; i < 8; i++) {
+                  const float2 y = cmul(yv[h0 + i], o_ph);             // the block's LO phase rides the gain multiply
+                  float2 z = make_float2(y.x * gn[i], y.y * gn[i]);  // linear.c:280
+                  if (o_shc != 0.0) {  // post-detection shift oscillator (linear.c:283-289, osc.c:39-51)
+                    double ps = o_shp + o_shc * (double)(32 * k + i0 + i);
+                    ps -= floor(ps);
+                    double sn, cs;
+                    sincospi(2.0 * ps, &sn, &cs);
+                    z = cmul(z, make_float2((float)cs, (float)sn));
+                  }
+                  out[2 * i] = scaleclip(z.x);
+                  out[2 * i + 1] = scaleclip(z.y);
+                }
+                if (i0 + 8 <= cnt && (olen & 7) == 0) {  // whole group inside the block, rows 16-byte aligned: 128-bit stores
+                  if (o_nch == 1) {   // mono: I only (linear.c:291-296)
+                    uint4 w;
+                    w.x = (unsigned short)out[0] | ((unsigned)(unsigned short)out[2] << 16);
+                    w.y = (unsigned short)out[4] | ((unsigned)(unsigned short)out[6] << 16);
+                    w.z = (unsigned short)out[8] | ((unsigned)(unsigned short)out[10] << 16);
+                    w.w = (unsigned short)out[12] | ((unsigned)(unsigned short)out[14] << 16);
+                    *reinterpret_cast<uint4*>(row + i0) = w;
+                  } else {  // I left, Q right (linear.c:299)
+                    uint4 w0, w1;
+                    w0.x = (unsigned short)out[0] | ((unsigned)(unsigned short)out[1] << 16);
+                    w0.y = (unsigned short)out[2] | ((unsigned)(unsigned short)out[3] << 16);
+                    w0.z = (unsigned short)out[4] | ((unsigned)(unsigned short)out[5] << 16);
+                    w0.w = (unsigned short)out[6] | ((unsigned)(unsigned short)out[7] << 16);
+                    w1.x = (unsigned short)out[8] | ((unsigned)(unsigned short)out[9] << 16);
+                    w1.y = (unsigned short)out[10] | ((unsigned)(unsigned short)out[11] << 16);
+                    w1.z = (unsigned short)out[12] | ((unsigned)(unsigned short)out[13] << 16);
+                    w1.w = (unsigned short)out[14] | ((unsigned)(unsigned short)out[15] << 16);
+                    *reinterpret_cast<uint4*>(row + 2 * i0) = w0;
+                    *reinterpret_cast<uint4*>(row + 2 * i0 + 8) = w1;
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; i++)
+                    if (i0 + i < cnt) {
+                      if (o_nch == 1) {
+                        row[i0 + i] = out[2 * i];
+                      } else {
+                        row[2 * (i0 + i)] = out[2 * i];
+                        row[2 * (i0 + i) + 1] = out[2 * i + 1];
+                      }
+                    }
+                }
               }
             }
           }
@@ -1277,11 +1307,17 @@ __global__ void __launch_bounds__(SER_THREADS) agc_serial_kernel(const ChanLaunc
       }
     }
     if (LINEAR && role == 4 && T + 1 >= 0 && T + 1 < ntiles && pT == T + 1) {
-      // the kept filter-output samples of the tile this warp handles NEXT step, into registers (row r = channel w0 + r)
-      const int pcnt = min(32, olen - 32 * pk);
-      const float2* g = a.agc_y + ((long long)pb * a.nwork + w0) * olen + 32 * pk + lane;
+      // this lane's channel: this warp's eight kept filter-output samples of the tile handled NEXT step, as four 128-bit
+      // loads (64 contiguous bytes per lane; the guard keeps the last tile of a block inside its row)
+      if (c >= 0) {
+        const float4* g = reinterpret_cast<const float4*>(a.agc_y + ((long long)pb * a.nwork + w) * olen + 32 * pk + 8 * ow);
 #pragma unroll
-      for (int r = 0; r < 32; r++) yv[r] = (r < nrows && lane < pcnt) ? __ldg(g + (long long)r * olen) : make_float2(0.f, 0.f);
+        for (int j = 0; j < 4; j++) {
+          const float4 v = (32 * pk + 8 * ow + 2 * j + 1 < olen) ? __ldg(g + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          yv[2 * j] = make_float2(v.x, v.y);
+          yv[2 * j + 1] = make_float2(v.z, v.w);
+        }
+      }
       pT++;
       if (++pk == tpb) {
         pk = 0;
@@ -1397,7 +1433,7 @@ static int launch_agc(const ChanLaunch& a, cudaStream_t st) {
     agc_front_kernel<LINEAR, 960><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
   else
     agc_front_kernel<LINEAR, 0><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
-  agc_serial_kernel<LINEAR><<<(a.nwork + 31) / 32, SER_THREADS, sizeof(SerialShared), st>>>(a);
+  agc_serial_kernel<LINEAR><<<(a.nwork + 31) / 32, LINEAR ? SER_THREADS_LIN : SER_THREADS, sizeof(SerialShared), st>>>(a);
   // the recurrence kernel wrote the PCM (AM: (s - DC) * gain; linear: gain x LO phase x shift oscillator); only the
   // shift oscillators' phase is left to advance
   if (LINEAR) agc_shift_advance_kernel<<<(a.nwork + 127) / 128, 128, 0, st>>>(a);
