@@ -247,6 +247,93 @@ def run_reference(args, plan, emit=True):
     return line
 
 
+def _resident_class_times(c, in_ptr, B, steps=20):
+    """prime the ring, then time `steps` resident steps with the FFT/channel overlap off: ms per step by kernel class"""
+    for _ in range(2):
+        c.push(in_ptr, B)
+        c.compute(B)
+        c.sync()
+    for _ in range(10):
+        c.compute_resident(B)
+    c.sync()
+    c.set_overlap(False)
+    for _ in range(3):
+        c.compute_resident(B)
+    c.sync()
+    c.timer_start()
+    for _ in range(steps):
+        c.compute_resident(B)
+    ms, classes = c.timer_stop()
+    return ms / steps, {k: v[0] / steps for k, v in classes.items()}
+
+
+def run_other_workloads(args, plan5, pin_in, B):
+    import ctypes as C
+    from ka9q_sdr_b200 import channelizer as ch, frontend, modes, workloads
+    peak, _ = measured_peak_hbm()
+    out = []
+    olen = plan5.L // plan5.D
+    in_ptr = C.c_void_p(pin_in.ptr)
+    # 8192 channels of one AM / linear mode on the cfg5 stream
+    for mode, cls in (("AM", "am"), ("USB", "linear")):
+        c = ch.Channelizer(plan5.samprate, plan5.L, plan5.M, plan5.D, max_blocks=B)
+        for spec in plan5.channels:
+            c.add_channel(mode, spec.bin)
+        c.commit()
+        ms, cm = _resident_class_times(c, in_ptr, B)
+        m = modes.get_mode(mode)
+        nbytes = len(plan5.channels) * B * workloads.channel_block_bytes(m.demod_type, 1, olen)
+        out.append({"workload": f"{len(plan5.channels)}x {mode} on the cfg5 stream", "blocks_per_step": B, "ms_per_step": ms,
+                    "value": len(plan5.channels) * (B * plan5.L / 1e6) / (ms / 1e3), "unit": UNIT,
+                    "kernel_ms": cm[cls], "kernels": "agc_front_kernel + agc_serial_kernel",
+                    "roofline": {"bound": "hbm", "achieved": nbytes / (cm[cls] / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": nbytes / (cm[cls] / 1e3) / 1e9 / peak, "algorithmic_bytes_per_step": nbytes}})
+        c.close()
+    # cfg4: 1024 mixed channels at 19.2 MS/s (N = 819 200)
+    p4 = workloads.cfg4()
+    iq4 = ch.PinnedBuffer(B * p4.L * 4, np.int16)
+    iq4.array[:] = make_input(p4, B)
+    c = ch.Channelizer(p4.samprate, p4.L, p4.M, p4.D, max_blocks=B)
+    for spec in p4.channels:
+        c.add_channel(spec.mode, spec.bin)
+    c.commit()
+    ms, cm = _resident_class_times(c, C.c_void_p(iq4.ptr), B)
+    nb4 = sum(workloads.channel_block_bytes(modes.get_mode(s_.mode).demod_type, 1, olen) for s_ in p4.channels) * B
+    out.append({"workload": p4.name, "blocks_per_step": B, "ms_per_step": ms,
+                "value": len(p4.channels) * (B * p4.L / 1e6) / (ms / 1e3), "unit": UNIT, "class_ms_per_step": cm,
+                "speedup_over_realtime": B * 20.0 / ms,
+                "note": "FM, AM and linear kernels run concurrently on three streams; ms_per_step is the serialised sum "
+                        "of forward FFT and channel kernels",
+                "roofline": {"bound": "hbm", "achieved": nb4 / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": nb4 / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_step": nb4,
+                             "what": "all channel kernels + forward FFT of the step"}})
+    c.close()
+    iq4.free()
+    # K5: front-end decimator service, /64 (12.288 MS/s int8 -> 192 kS/s int16 in the reference's hackrf set-up)
+    cb, nblk = 131072, 64
+    n = cb * nblk
+    rng = np.random.default_rng(11)
+    iq8 = rng.integers(-40, 40, 2 * n, dtype=np.int8)
+    fe = frontend.Frontend(192000, 64, 1, cb)
+    fe.set_estimates(0.0, 0.0, 1.0, 0.0)
+    fe.process(iq8)
+    for _ in range(3):
+        fe.rerun_resident(n)
+    t = [fe.rerun_resident(n) for _ in range(10)]
+    ms = float(np.median(t))
+    fbytes = n * 2 + (n // 64) * 4
+    out.append({"workload": "front-end decimator service: int8 I/Q, DC / gain / phase correction, Fs/4 rotation, /64 half-band "
+                            "cascade on both planes, int16 out (hackrf.c:129-345)", "input_samples_per_step": n,
+                "ms_per_step": ms, "value": n / 1e6 / (ms / 1e3), "unit": "MS/s (input rate)",
+                "launches_per_step": nblk + 1, "reference_published": "14.8 MS/s per Atom core for the /64 cascade (dcc2018.pdf p.9)",
+                "roofline": {"bound": "hbm", "achieved": fbytes / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": fbytes / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_step": fbytes,
+                             "what": "2 B in + 4/64 B out per complex input sample; the estimate chain (one launch per "
+                                     "131072-sample callback block) is launch-bound, not bandwidth-bound"}})
+    fe.close()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 
 def run_ours(args, plan):
@@ -433,6 +520,17 @@ def run_ours(args, plan):
         b1 = {"blocks_per_step": 1, "ms_per_step": ms1 / n1, "value": K * (plan.L / 1e6) / (ms1 / n1 / 1e3), "unit": UNIT,
               "speedup_over_realtime": 20.0 / (ms1 / n1)}
 
+    # ---- other workloads of the path, device-resident, each with its own HBM-roofline fraction (N = 1 only): 8192 AM and
+    # 8192 USB channels on the same stream (the AM / linear kernels), cfg4 (1024 mixed FM/FM/AM/USB channels at 19.2 MS/s),
+    # and the front-end decimator service (K5: int8 in, /64, int16 out)
+    others = None
+    if not multi and args.extras:
+        others = []
+        try:
+            others = run_other_workloads(args, plan, pin_in, B)
+        except Exception as e:   # the headline numbers stand on their own
+            others = [{"error": str(e)}]
+
     # ---- end-to-end leg (host pinned buffers, H2D + D2H inside the timed region)
     c.sync()
     if sharded:
@@ -592,6 +690,8 @@ def run_ours(args, plan):
     }
     if b1:
         line["operating_points"] = [b1]
+    if others:
+        line["other_workloads"] = others
     if weak:
         line["weak"] = weak
     if sharded:
@@ -625,6 +725,8 @@ def main():
                          "spectrum all-gathered / broadcast by NCCL")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="sharded mode: exchange transport")
     ap.add_argument("--no-weak", dest="weak", action="store_false", help="skip the weak-scaling line of multi-GPU runs")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="skip the other workloads (AM / USB at scale, cfg4, front-end service) of the N = 1 run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     plan = make_plan(args.config, args.channels)
