@@ -245,6 +245,8 @@ int ka9q_stream_compute(ka9q_stream *s, int nblocks);
 int ka9q_stream_compute_resident(ka9q_stream *s, int nblocks);
 int ka9q_stream_fetch(ka9q_stream *s, int nblocks, int16_t *pcm, ka9q_chan_status *status);
 int ka9q_stream_sync(ka9q_stream *s);
+/* wait only until the H2D copies of push / push_at have finished reading their host buffers (e.g. before ka9q_rx_consume) */
+int ka9q_stream_sync_input(ka9q_stream *s);
 /* wait only for the D2H copies issued by ka9q_stream_fetch (PCM/status are double-buffered on the device, so the next
  * batch may already be computing): the steady-state loop is push(k+2); compute(k+1); fetch(k); wait_fetch() */
 int ka9q_stream_wait_fetch(ka9q_stream *s);

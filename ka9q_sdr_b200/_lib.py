@@ -81,7 +81,7 @@ EXPORTED = [
     "ka9q_stream_enable_n0", "ka9q_stream_fetch_n0", "ka9q_frontend_create", "ka9q_frontend_destroy",
     "ka9q_frontend_process", "ka9q_frontend_process_to_stream", "ka9q_frontend_rerun_resident",
     "ka9q_frontend_set_estimates", "ka9q_frontend_get_status", "ka9q_stream_push_device",
-    "ka9q_rx_create", "ka9q_rx_destroy", "ka9q_rx_inject", "ka9q_rx_drain", "ka9q_rx_start", "ka9q_rx_stop",
+    "ka9q_stream_sync_input", "ka9q_rx_create", "ka9q_rx_destroy", "ka9q_rx_inject", "ka9q_rx_drain", "ka9q_rx_start", "ka9q_rx_stop",
     "ka9q_rx_peek_blocks", "ka9q_rx_consume", "ka9q_rx_blocks_ready", "ka9q_rx_get_stats", "ka9q_pcm_send_block",
 ]
 
@@ -153,6 +153,7 @@ def lib():
     L.ka9q_frontend_set_estimates.argtypes = [vp, cf, cf, cf, cf]
     L.ka9q_frontend_get_status.argtypes = [vp, C.POINTER(FrontendStatus)]
     L.ka9q_stream_push_device.argtypes = [vp, vp, cll]
+    L.ka9q_stream_sync_input.argtypes = [vp]
     L.ka9q_rx_create.argtypes = [ci, cll, ci]
     L.ka9q_rx_create.restype = vp
     L.ka9q_rx_destroy.argtypes = [vp]

@@ -19,19 +19,13 @@
 // Results equal the single-GPU run: AM / linear bit for bit, FM within 1 LSB where the pair partner differs.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
 #include "stream_priv.cuh"
 
 namespace {
-
-struct CopyJob {  // 16-byte units
-  const int4* src;
-  int4* dst;
-  long long n16;
-  long long first;  // index of this job's first unit in the concatenation of all jobs
-};
 
 constexpr int SCATTER_THREADS = 256;
 constexpr long long SPIN_TIMEOUT_CYCLES = 6000000000ll;  // ~3 s: a dead peer must not hang the GPU
@@ -106,6 +100,14 @@ __global__ void mgpu_wait_kernel(MgpuFlags* flags, int which /* 0 ready, 1 freed
       break;
     }
   }
+}
+
+// producer -> consumers after copy-engine transfers: the arcs of batch seq have landed in every peer's buffer p
+__global__ void mgpu_signal_ready_kernel(MgpuFlags* const* peer_flags, int nranks, int me, int p, int seq) {
+  const int r = threadIdx.x;
+  if (r >= nranks || r == me) return;
+  __threadfence_system();
+  st_release_sys(&peer_flags[r]->ready[p][me], seq);
 }
 
 // consumer -> producers: this rank has finished reading its spectrum buffer p for batch seq
@@ -325,6 +327,10 @@ static int exchange_p2p(ka9q_stream* s, int nblocks, int p, int seq) {
       }
     K9_CHECK(jobs[0].size() <= 32, "too many exchange segments (max 32 per batch)");
     s->mg_njobs = (int)jobs[0].size();
+    for (int par = 0; par < 2; par++) {
+      s->mg_host_jobs[par].clear();
+      for (const CopyJob& j : jobs[par]) s->mg_host_jobs[par].push_back(j);
+    }
     if (s->d_mg_jobs) cudaFree(s->d_mg_jobs);
     s->d_mg_jobs = nullptr;
     if (s->mg_njobs) {
@@ -336,8 +342,24 @@ static int exchange_p2p(ka9q_stream* s, int nblocks, int p, int seq) {
   }
   // the peers have finished reading their buffer p of two batches ago
   if (seq > 2) mgpu_wait_kernel<<<1, 32, 0, s->s_fft>>>(s->d_flags, 1, p, G, me, seq - 2);
-  // a few CTAs per SM is plenty for NVLink (~0.8 TB/s) and leaves the SMs to the channel kernels of the previous batch
-  mgpu_scatter_kernel<<<148, SCATTER_THREADS, 0, s->s_fft>>>((const CopyJob*)s->d_mg_jobs + (size_t)p * s->mg_njobs, s->mg_njobs,
+  static int ctas = 0, use_ce = -1;
+  if (!ctas) {
+    const char* e = getenv("KA9Q_B200_SCATTER_CTAS");
+    ctas = e && atoi(e) > 0 ? atoi(e) : 592;
+    e = getenv("KA9Q_B200_MGPU_CE");
+    use_ce = e && atoi(e) != 0;
+  }
+  if (use_ce) {
+    // KA9Q_B200_MGPU_CE=1: the arcs go through the copy engines (peer-to-peer cudaMemcpyAsync, no SM involved), then a
+    // one-warp kernel raises the flags; kept as the measured alternative to the copy kernel
+    const std::vector<CopyJob>& hj = s->mg_host_jobs[p];
+    for (const CopyJob& j : hj)
+      K9_CUDA(cudaMemcpyAsync(j.dst, j.src, (size_t)j.n16 * 16, cudaMemcpyDeviceToDevice, s->s_fft));
+    mgpu_signal_ready_kernel<<<1, 32, 0, s->s_fft>>>(s->d_mg_peer_flag_ptrs, G, me, p, seq);
+    K9_CHECK(cudaGetLastError() == cudaSuccess, "signal kernel launch failed");
+    return 0;
+  }
+  mgpu_scatter_kernel<<<ctas, SCATTER_THREADS, 0, s->s_fft>>>((const CopyJob*)s->d_mg_jobs + (size_t)p * s->mg_njobs, s->mg_njobs,
                                                             s->d_mg_counter, s->d_mg_peer_flag_ptrs, G, me, p, seq);
   K9_CHECK(cudaGetLastError() == cudaSuccess, "scatter kernel launch failed");
   return 0;

@@ -871,6 +871,14 @@ int ka9q_stream_wait_fetched(ka9q_stream* s, int batches_ago) {
   return 0;
 }
 
+// Wait until every H2D copy issued by push / push_at has finished reading its host buffer (the compute may still run).
+int ka9q_stream_sync_input(ka9q_stream* s) {
+  K9_CHECK(s && s->committed, "stream not committed");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  K9_CUDA(cudaStreamSynchronize(s->s_in));
+  return 0;
+}
+
 int ka9q_stream_sync(ka9q_stream* s) {
   K9_CHECK(s && s->committed, "stream not committed");
   K9_CUDA(cudaSetDevice(s->cfg.device));

@@ -21,6 +21,12 @@ struct MgpuFlags {                       // lives in device memory of every rank
   int error;                             // a wait timed out
   int pad[31];
 };
+struct CopyJob {                         // one arc of one block for one peer, in 16-byte units
+  const int4* src;
+  int4* dst;
+  long long n16;
+  long long first;                       // index of this job's first unit in the concatenation of all jobs
+};
 struct MgpuSeg {                         // one contiguous piece of a rank's needed arc, in bins
   long long lo, len;
 };
@@ -106,6 +112,7 @@ struct ka9q_stream {
   void* d_mg_jobs = nullptr;                         // copy-job list of the scatter kernel
   unsigned* d_mg_counter = nullptr;                  // CTAs of the scatter kernel that have finished
   int mg_njobs = 0, mg_jobs_nblocks = 0;
+  std::vector<CopyJob> mg_host_jobs[2];              // host copy of the job lists (copy-engine transport)
   int mg_wait_ready = 0;                             // sequence number the next channel launch has to wait for (P2P)
   MgpuFlags** d_mg_peer_flag_ptrs = nullptr;         // device copy of mg_peer_flags
   // live timing of the timed region (bench.py): event pairs around every forward FFT and every FM/AM/linear launch
