@@ -148,3 +148,21 @@ def test_make_kaiser_matches_reference_golden():
         np.testing.assert_allclose(w, g[key], rtol=2e-6, atol=1e-7)
         if M & 1:
             assert w[(M - 1) // 2] == 1.0
+
+
+def test_oscillator_chirp_matches_reference(ref):
+    """The Doppler form of the oscillator: a non-zero sweep rate makes phasor_step itself step (osc.c:31-34,44-46) and
+    renorm_osc normalise both (osc.c:57-58). Checked against the verbatim reference across two renormalisations, for the
+    rates set_doppler produces (radio.c:180-184: -rate / samprate^2) and for a zero start frequency."""
+    for f, r in ((-1500.0 / 192000, -40.0 / 192000 ** 2), (0.0, 3e-9), (0.123, -2.5e-8)):
+        n = 40000
+        out = np.zeros(2 * n)
+        assert _lib.lib().ka9q_osc_run(f, r, n, out.ctypes.data_as(C.c_void_p)) == 0
+        got = out[0::2] + 1j * out[1::2]
+        want = ref.osc_run(f, r, n)
+        # a one-ulp difference in cos / sin of the tiny sweep angle (libm vs gcc's -funsafe-math code in the reference) is a
+        # step-of-the-step error and grows with n^2 / 2 = 8e8: 1.5e-8 after 40 000 steps is that, not an algorithmic difference
+        np.testing.assert_allclose(got, want, rtol=0, atol=5e-8)
+        np.testing.assert_allclose(got[:2000], want[:2000], rtol=0, atol=5e-10)      # (n^2 / 2 = 2e6 there)
+        if f != 0.0:
+            assert abs(np.angle(got[-1] * np.conj(got[-2])) / (2 * np.pi) - (f + r * (n - 2))) < 1e-9   # it really sweeps
