@@ -214,6 +214,10 @@ int ka9q_stream_commit(ka9q_stream *s);
 /* Re-design one channel's filter after commit (the UI path: display.c:163-177). */
 int ka9q_stream_set_filter(ka9q_stream *s, int chan, float low, float high, float kaiser_beta);
 
+/* PL-tone analyser (pltask, fm.c:189-285) for every de-emphasised FM channel: a /32 REAL slave of the audio master filter
+ * feeding a 16384-point transform every 0.34 s. Enable before commit; the tone frequency (demod->sig.plfreq: 0 until the
+ * first analysis, NAN when no tone stands out) is ka9q_chan_status.reserved[1] of FM channels. */
+int ka9q_stream_enable_pl(ka9q_stream *s, int enable);
 /* Noise-density estimate compute_n0 (radio.c:383-425; fm.c:78-82, am.c:46-49, linear.c:123-126) for every channel and
  * block, computed once per stream on the device (csrc/n0.cu). Enable before commit; rows are fetched like the PCM. */
 int ka9q_stream_enable_n0(ka9q_stream *s, int enable);

@@ -88,6 +88,10 @@ class Channelizer:
         self.channels.append(int(p.channels) if m.demod_type == LINEAR_DEMOD else 1)
         return idx
 
+    def enable_pl(self, enable: bool = True):
+        """PL-tone analyser (fm.c:189-285) for the FM channels; call before commit. plfreq = status['reserved'][..., 1]."""
+        _lib.check(self.lib.ka9q_stream_enable_pl(self.h, 1 if enable else 0), "enable_pl")
+
     def enable_n0(self, enable: bool = True):
         """compute_n0 (radio.c:383-425) for every channel and block; call before commit."""
         _lib.check(self.lib.ka9q_stream_enable_n0(self.h, 1 if enable else 0), "enable_n0")

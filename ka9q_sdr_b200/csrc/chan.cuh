@@ -62,6 +62,17 @@ struct PllState {
   int pad_;
 };
 
+// PL-tone analyser (fm.c:189-285): one work item per de-emphasised FM channel
+struct PlWork {
+  int chan, pair, half;  // channel index, index of its pair in the FM work list, 0 = the pair's first channel (real part)
+  int pad_;
+};
+struct PlState {
+  int fft_ptr, last_fft;  // fm.c:231-232
+  float plfreq;           // demod->sig.plfreq
+  int pad_;
+};
+
 struct ChanStatus {      // mirrors the demod->sig.* scalars the reference demodulators publish
   float bb_power;        // fm.c:99, am.c:78, linear.c:302
   float snr;             // fm.c:102-103 (NAN for AM / non-PLL linear, linear.c:309)
@@ -108,6 +119,13 @@ struct ChanLaunch {
   const PllParams* pll_params;
   PllState* pll_state;
   float2* pll_ring;          // [npll][65536] carrier-search ring (linear.c:84-93)
+  // PL-tone analyser (optional)
+  float2* pl_spec;           // [nblocks][pl_npairs][65]: low bins of every pair's audio transform, written by fm_kernel
+  int pl_npairs;
+  const PlWork* pl_work;
+  PlState* pl_state;
+  float* pl_ring;            // [npl][16384]
+  const float2* pl_resp;     // [33] slave response (fm.c:208-218)
 };
 
 // mixed: AM / linear kernels of the same stream run beside this one (they need the maximum shared-memory carve-out; CTAs
@@ -118,5 +136,6 @@ int fm_carveout(bool mixed);
 int launch_am(const ChanLaunch& a, cudaStream_t st);
 int launch_linear(const ChanLaunch& a, cudaStream_t st);
 int launch_pll(const ChanLaunch& a, cudaStream_t st);
+int launch_pl(const ChanLaunch& a, int nchan_pl, cudaStream_t st);
 
 }  // namespace k9

@@ -617,6 +617,11 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
                         (ringbase + first) & (NDEC - 1));
         if (t == 0) sh.ephase[h] = phase_advance(e, sh.P[h].phase_step, a.N);
       } else if (job == 2) {
+        if (a.pl_spec) {  // PL-tone analyser enabled: the low bins of Z = FFT(audA + j audB) for pl_kernel (Z = conj(v))
+          float2* o = a.pl_spec + ((long long)b * a.pl_npairs + blockIdx.x) * 65;
+          if (t <= 32) o[t] = make_float2(v[0].x, -v[0].y);
+          if (t >= 96) o[33 + 127 - t] = make_float2(v[15].x, -v[15].y);  // Z[2048 - k], k = 128 - t
+        }
         const float2* R = a.audio_resp + (long long)sh.P[0].audio_slot * NDEC + t;
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -1354,6 +1359,7 @@ __global__ void agc_shift_advance_kernel(const ChanLaunch a) {
 
 }  // namespace k9
 #include "pll_kernel.cuh"
+#include "pl_kernel.cuh"
 namespace k9 {
 
 // ---------------------------------------------------------------- launchers

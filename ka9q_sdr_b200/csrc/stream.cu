@@ -470,6 +470,38 @@ static int commit_impl(ka9q_stream* s) {
     }
     if (rows_am + rows_lin) K9_CUDA(cudaMalloc(&s->d_agc_pow, sizeof(float) * 2 * (rows_am + rows_lin)));
   }
+  if (s->pl_enabled && !w_fm.empty()) {
+    // PL-tone analyser: one work item per de-emphasised FM channel (FLAT channels have no audio transform to tap)
+    std::vector<PlWork> pw;
+    for (size_t i = 0; i < w_fm.size(); i++) {
+      const int ca = w_fm[i].x, cb = w_fm[i].y;
+      if (s->h_params[ca].audio_slot < 0) continue;
+      pw.push_back(PlWork{ca, (int)i, 0, 0});
+      if (cb >= 0) pw.push_back(PlWork{cb, (int)i, 1, 0});
+    }
+    s->n_pl = (int)pw.size();
+    if (s->n_pl) {
+      K9_CUDA(cudaMalloc(&s->d_pl_work, sizeof(PlWork) * s->n_pl));
+      K9_CUDA(cudaMemcpy(s->d_pl_work, pw.data(), sizeof(PlWork) * s->n_pl, cudaMemcpyHostToDevice));
+      K9_CUDA(cudaMalloc(&s->d_pl_state, sizeof(PlState) * s->n_pl));
+      K9_CUDA(cudaMemset(s->d_pl_state, 0, sizeof(PlState) * s->n_pl));  // struct demod is zero-initialised: plfreq = 0
+      K9_CUDA(cudaMalloc(&s->d_pl_ring, sizeof(float) * (size_t)s->n_pl * 16384));
+      K9_CUDA(cudaMemset(s->d_pl_ring, 0, sizeof(float) * (size_t)s->n_pl * 16384));
+      K9_CUDA(cudaMalloc(&s->d_pl_spec, sizeof(float2) * (size_t)B * w_fm.size() * 65));
+      K9_CUDA(cudaMemset(s->d_pl_spec, 0, sizeof(float2) * (size_t)B * w_fm.size() * 65));
+      // slave response (fm.c:200-218): PL_N = AN/32 = 64, PL_L = AL/32, PL_M = PL_N - PL_L + 1; unity below 300 Hz on the
+      // positive side, Kaiser beta 2, through the library's own window_rfilter
+      const int PL_N = NDEC / 32, PL_L = s->olen / 32, PL_M = PL_N - PL_L + 1;
+      std::vector<float2> pr(PL_N / 2 + 1, make_float2(0.f, 0.f));
+      for (int j = 0; j <= PL_N / 2; j++) {
+        float const f = (float)j * dsamprate / NDEC;
+        if (f > 0 && f < 300) pr[j].x = 1;
+      }
+      K9_CHECK(window_rfilter(PL_L, PL_M, pr.data(), 2.0f) == 0, "PL response design failed: %s", get_error());
+      K9_CUDA(cudaMalloc(&s->d_pl_resp, sizeof(float2) * pr.size()));
+      K9_CUDA(cudaMemcpy(s->d_pl_resp, pr.data(), sizeof(float2) * pr.size(), cudaMemcpyHostToDevice));
+    }
+  }
   if (any_fm) {
     // one ring per channel + a spare all-zero ring that stands in for the missing partner of an unpaired FM channel
     K9_CUDA(cudaMalloc(&s->d_audio_hist, sizeof(float) * (size_t)(K + 1) * NDEC));
@@ -525,6 +557,15 @@ int ka9q_stream_set_filter(ka9q_stream* s, int chan, float low, float high, floa
     s->h_params[chan].fm_gain = (p.headroom * M_1_PI * dsamprate) / fabsf(p.low - p.high);
   }
   K9_CUDA(cudaMemcpy(s->d_params + chan, &s->h_params[chan], sizeof(ChanParams), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// PL-tone analyser (pltask, fm.c:189-285) for every de-emphasised FM channel; call before commit. The tone frequency
+// (demod->sig.plfreq: 0 until the first analysis, NAN when no tone stands out) is status row field reserved[1].
+int ka9q_stream_enable_pl(ka9q_stream* s, int enable) {
+  K9_CHECK(s, "null argument");
+  K9_CHECK(!s->committed, "ka9q_stream_enable_pl must be called before commit");
+  s->pl_enabled = enable != 0;
   return 0;
 }
 
@@ -753,8 +794,19 @@ int issue_channels(ka9q_stream* s, int nblocks) {
   if (s->n_fm) {
     a.work = s->d_work_fm;
     a.nwork = s->n_fm;
-    TimedRegion tr(s, TC_FM, s->s_comp);
-    K9_CHECK(launch_fm(a, s->s_comp, s->n_am + s->n_lin + s->n_pll > 0) == 0, "fm kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (s->n_pl) {
+      a.pl_spec = s->d_pl_spec;
+      a.pl_npairs = s->n_fm;
+      a.pl_work = s->d_pl_work;
+      a.pl_state = s->d_pl_state;
+      a.pl_ring = s->d_pl_ring;
+      a.pl_resp = s->d_pl_resp;
+    }
+    {
+      TimedRegion tr(s, TC_FM, s->s_comp);
+      K9_CHECK(launch_fm(a, s->s_comp, s->n_am + s->n_lin + s->n_pll > 0) == 0, "fm kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (s->n_pl) K9_CHECK(launch_pl(a, s->n_pl, s->s_comp) == 0, "pl kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (s->n0_enabled) {
     // K6 beside the channel kernels: reads the same spectrum buffer, writes the n0 rows of this batch
@@ -973,6 +1025,7 @@ static void release_resources(ka9q_stream* s) {
                   (void**)&s->d_params, (void**)&s->d_state, (void**)&s->d_resp, (void**)&s->d_audio_resp,
                   (void**)&s->d_audio_hist, (void**)&s->d_pcm, (void**)&s->d_status, (void**)&s->d_filt,
                   (void**)&s->d_windows, (void**)&s->d_work_fm, (void**)&s->d_work_am, (void**)&s->d_work_lin,
+                  (void**)&s->d_pl_spec, (void**)&s->d_pl_resp, (void**)&s->d_pl_work, (void**)&s->d_pl_state, (void**)&s->d_pl_ring,
                   (void**)&s->d_work_pll, (void**)&s->d_pll_params, (void**)&s->d_pll_state, (void**)&s->d_pll_ring,
                   (void**)&s->d_n0_chan, (void**)&s->d_n0_P, (void**)&s->d_n0_T, (void**)&s->d_n0_list, (void**)&s->d_n0_raw,
                   (void**)&s->d_n0_smooth, (void**)&s->d_n0_state, (void**)&s->d_n0_partial, (void**)&s->d_n0_blk};

@@ -89,6 +89,13 @@ struct ka9q_stream {
   bool fft_pending = false;
   int fft_blocks_per_launch = 0;  // 0 = all blocks of the batch in one launch per pass (measured faster than per-block)
   bool overlap = true;  // false: the forward FFT waits for the previous batch's channel kernels (per-kernel timing)
+  // PL-tone analyser (pl_kernel.cuh): enabled by ka9q_stream_enable_pl before commit
+  bool pl_enabled = false;
+  int n_pl = 0;
+  float2 *d_pl_spec = nullptr, *d_pl_resp = nullptr;
+  PlWork* d_pl_work = nullptr;
+  PlState* d_pl_state = nullptr;
+  float* d_pl_ring = nullptr;
   // K6 noise density (n0.cu): enabled by ka9q_stream_enable_n0 before commit
   bool n0_enabled = false;
   cudaStream_t s_n0 = nullptr;

@@ -53,6 +53,8 @@ struct ref_block_status {
   float bb_power, snr, foffset, pdeviation, if_power, n0, agc_gain, cphase;
   int pll_lock;
   int channels;
+  float plfreq;   /* demod->sig.plfreq as pltask (fm.c:189-285) left it when the block's PCM was sent */
+  int pad;
 };
 
 struct capture {
@@ -110,6 +112,7 @@ static void capture_block(struct demod *demod, const float *buffer, int nfloats,
     s->agc_gain = demod->agc.gain;
     s->cphase = demod->sig.cphase;
     s->pll_lock = demod->sig.pll_lock;
+    s->plfreq = demod->sig.plfreq;
     s->channels = channels;
   }
   c->nblocks++;

@@ -30,7 +30,7 @@ class RefBlockStatus(C.Structure):
     _fields_ = [
         ("bb_power", C.c_float), ("snr", C.c_float), ("foffset", C.c_float), ("pdeviation", C.c_float),
         ("if_power", C.c_float), ("n0", C.c_float), ("agc_gain", C.c_float), ("cphase", C.c_float),
-        ("pll_lock", C.c_int), ("channels", C.c_int),
+        ("pll_lock", C.c_int), ("channels", C.c_int), ("plfreq", C.c_float), ("pad", C.c_int),
     ]
 
 

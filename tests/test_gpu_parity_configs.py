@@ -287,3 +287,45 @@ def test_coherent_pll_modes_against_reference(ref, mode):
     if mode != "CISB":
         assert rs["pll_lock"][-1] == 1          # the loop did lock on this stimulus
     c.close()
+
+
+def test_pl_tone_analyser_matches_reference(ref):
+    """pltask (fm.c:189-285): /32 slave of the audio master, 16384-point transform every 512 samples, strongest bin reported
+    as sig.plfreq. Three NBFM channels — 103.5 Hz and 131.8 Hz sub-audible tones under a 1 kHz voice tone, and one without —
+    so that both halves of a channel pair and an unpaired channel are analysed. The reference's pltask is its own thread,
+    one block behind or level with the demodulator, so the onset is compared to +-2 blocks and the value once it has
+    settled (one transform bin is 0.092 Hz)."""
+    fs = 192000
+    D, L, M, N = synth.geometry(fs)
+    nb = 80
+    n = nb * L
+    t = np.arange(n) / fs
+    rng = np.random.default_rng(2)
+    bins = [2048, -1536, 512]
+    pl = [103.5, 131.8, None]
+    x = synth.awgn(rng, n, 0.02)
+    for k, f in zip(bins, pl):
+        ph = 2 * np.pi * k * fs / N * t + 2.5 * np.sin(2 * np.pi * 1000 * t)
+        if f:
+            ph = ph + (600 / f) * np.sin(2 * np.pi * f * t)
+        x = x + 0.2 * np.exp(1j * ph)
+    iq = synth._quantize(x)
+    c = ch.Channelizer(fs, L, M, D, max_blocks=4)
+    c.enable_pl()
+    for k in bins:
+        c.add_channel("FM", k)
+    c.commit()
+    pcm, st = c.run(iq)
+    got = st["reserved"][:, :, 1]
+    for j, k in enumerate(bins):
+        r = ref.chain_run("FM", fs, L, M, D, iq, carrier_hz=k * fs / N, lo_cycles=-k / N)
+        want = r.status["plfreq"][:nb]
+        check_pcm("FM", c.channel_pcm(pcm, j), r.pcm, L // D, label=f"ch{j} ")      # the tap does not disturb the audio path
+        if pl[j]:
+            assert abs(got[-1, j] - pl[j]) < 0.1 and got[-1, j] == want[-1], (j, got[-1, j], want[-1])
+            on_g, on_r = int(np.argmax(got[:, j] > 0)), int(np.argmax(want > 0))
+            assert abs(on_g - on_r) <= 2 and on_g == 17, (on_g, on_r)    # 18 blocks x 30 samples = 540 >= 512
+            assert np.array_equal(got[on_g + 2:, j], want[on_g + 2:])
+        else:
+            assert np.isnan(got[-1, j]) and np.isnan(want[-1])
+    c.close()
