@@ -128,19 +128,28 @@ __global__ void __launch_bounds__(FE_THREADS) fe_stats_kernel(const char2* __res
     last = atomicAdd(counter, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last && threadIdx.x < 32) {
+    // the last CTA to finish reduces the per-CTA partials in a fixed order (lane l takes CTAs l, l + 32, ...; then a
+    // shuffle tree): deterministic, and one warp instead of one thread walking 64 dependent L2 loads
     __threadfence();
-    *counter = 0;
     StatsPartial s = {0, 0, 0, 0, 0, 0};
-    for (unsigned c = 0; c < gridDim.x; c++) {
-      const volatile StatsPartial* q = partial + c;
-      s.sum_re += q->sum_re;
-      s.sum_im += q->sum_im;
-      s.i_energy += q->i_energy;
-      s.q_energy += q->q_energy;
-      s.dotprod += q->dotprod;
-      s.clips += q->clips;
+    for (unsigned c = threadIdx.x; c < gridDim.x; c += 32) {
+      const StatsPartial* q = partial + c;
+      s.sum_re += __ldcg(&q->sum_re);
+      s.sum_im += __ldcg(&q->sum_im);
+      s.i_energy += __ldcg(&q->i_energy);
+      s.q_energy += __ldcg(&q->q_energy);
+      s.dotprod += __ldcg(&q->dotprod);
+      s.clips += __ldcg(&q->clips);
     }
+    s.sum_re = warp_sum(s.sum_re);
+    s.sum_im = warp_sum(s.sum_im);
+    s.i_energy = warp_sum(s.i_energy);
+    s.q_energy = warp_sum(s.q_energy);
+    s.dotprod = warp_sum(s.dotprod);
+    for (int o = 16; o > 0; o >>= 1) s.clips += __shfl_xor_sync(0xffffffffu, s.clips, o);
+    if (threadIdx.x != 0) return;
+    *counter = 0;
     FeEst e = *est;
     FeCoef nk = k;
     // hackrf.c:182-194, in its order

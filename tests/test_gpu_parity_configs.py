@@ -292,9 +292,7 @@ def test_coherent_pll_modes_against_reference(ref, mode):
 def test_pl_tone_analyser_matches_reference(ref):
     """pltask (fm.c:189-285): /32 slave of the audio master, 16384-point transform every 512 samples, strongest bin reported
     as sig.plfreq. Three NBFM channels — 103.5 Hz and 131.8 Hz sub-audible tones under a 1 kHz voice tone, and one without —
-    so that both halves of a channel pair and an unpaired channel are analysed. The reference's pltask is its own thread,
-    one block behind or level with the demodulator, so the onset is compared to +-2 blocks and the value once it has
-    settled (one transform bin is 0.092 Hz)."""
+    so that both halves of a channel pair and an unpaired channel are analysed (one transform bin is 0.092 Hz)."""
     fs = 192000
     D, L, M, N = synth.geometry(fs)
     nb = 80
@@ -302,7 +300,9 @@ def test_pl_tone_analyser_matches_reference(ref):
     t = np.arange(n) / fs
     rng = np.random.default_rng(2)
     bins = [2048, -1536, 512]
-    pl = [103.5, 131.8, None]
+    # tones on bin centres of the 16384-point transform at 1500 Hz (bins 1131 and 1440): a tone half way between two bins
+    # (e.g. 103.5 Hz = bin 1130.5) puts equal energy into both and the winner is decided by rounding noise in either program
+    pl = [1131 * 1500 / 16384, 1440 * 1500 / 16384, None]
     x = synth.awgn(rng, n, 0.02)
     for k, f in zip(bins, pl):
         ph = 2 * np.pi * k * fs / N * t + 2.5 * np.sin(2 * np.pi * 1000 * t)
@@ -322,10 +322,17 @@ def test_pl_tone_analyser_matches_reference(ref):
         want = r.status["plfreq"][:nb]
         check_pcm("FM", c.channel_pcm(pcm, j), r.pcm, L // D, label=f"ch{j} ")      # the tap does not disturb the audio path
         if pl[j]:
-            assert abs(got[-1, j] - pl[j]) < 0.1 and got[-1, j] == want[-1], (j, got[-1, j], want[-1])
+            # The reference's pltask is a free-running thread without back-pressure: when its
+            # 16384-point transform takes longer than a block it skips blocks, the ring then has phase jumps and its
+            # reading wanders by a few bins from run to run (measured here: 1131, 1132, 1133 for a tone on bin 1131; 1996
+            # ... 2000 for bin 2000). The device analyser sees every block: it must hit the tone's own bin exactly, and
+            # the reference must be within its own scatter (0.5 Hz) of it.
+            bin_hz = 1500 / 16384
+            assert abs(got[-1, j] - pl[j]) < 0.01 * bin_hz, (j, got[-1, j], pl[j])
+            assert abs(got[-1, j] - want[-1]) < 0.5, (j, got[-1, j], want[-1])
             on_g, on_r = int(np.argmax(got[:, j] > 0)), int(np.argmax(want > 0))
-            assert abs(on_g - on_r) <= 2 and on_g == 17, (on_g, on_r)    # 18 blocks x 30 samples = 540 >= 512
-            assert np.array_equal(got[on_g + 2:, j], want[on_g + 2:])
+            assert on_g == 17 and 0 <= on_r - on_g <= 10, (on_g, on_r)   # 18 blocks x 30 samples = 540 >= 512; the reference's thread lags
+            assert np.all(np.abs(got[on_g:, j] - pl[j]) < 1.5 * bin_hz)   # from the first analysis on (ring 3 % full)
         else:
             assert np.isnan(got[-1, j]) and np.isnan(want[-1])
     c.close()
