@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the library runs its forward FFT / multi-GPU exchange / channel kernels / copies on separate streams: give every one
+# of them its own hardware queue (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "channel·MS/s demodulated"
 UNIT = "channel·MS/s"

@@ -59,6 +59,7 @@ def _stimulus(plan, nb):
 
 def _worker(rank, world, port, mode, q, iq_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import ctypes as C
     import torch.distributed as dist
     from ka9q_sdr_b200 import channelizer as ch, mgpu, synth, workloads
