@@ -493,6 +493,13 @@ void bigfft_plan_destroy(BigFftPlan* plan) {
 
 void bigfft_set_carveout(int pct) { set_pass128_carveout(pct); }
 
+bool bigfft_can_route(const BigFftPlan* plan) {
+  static const bool use128 = !(getenv("KA9Q_B200_FFT_R128") && atoi(getenv("KA9Q_B200_FFT_R128")) == 0);
+  const int p = plan->npass - 1;
+  return use128 && plan->npass >= 2 && plan->R1[p] == 10 && plan->R2[p] == 16 && (plan->N / 160) % 16 == 0 &&
+         (long long)plan->N < (1ll << 30);
+}
+
 int bigfft_exec(const BigFftPlan* plan, const BigFftIn& in, float2* out, long long out_batch_stride, float2* tmp0,
                 float2* tmp1, int batch, int sign, cudaStream_t stream) {
   const int N = plan->N;
@@ -534,6 +541,10 @@ int bigfft_exec(const BigFftPlan* plan, const BigFftIn& in, float2* out, long lo
     a.tw_lo = plan->tw_lo;
     a.tw_hi = plan->tw_hi;
     a.tw_r = plan->tw_r[p];
+    if (lastpass && in.route_mask && bigfft_can_route(plan)) {
+      a.route_mask = in.route_mask;
+      for (int r = 0; r < 16; r++) a.route_delta[r] = in.route_delta[r];
+    }
     static const bool use128 = !(getenv("KA9Q_B200_FFT_R128") && atoi(getenv("KA9Q_B200_FFT_R128")) == 0);
     cudaError_t e = use128 ? launch_pass128(plan->R1[p], plan->R2[p], a, batch, sign, stream) : cudaErrorNotSupported;
     if (e == cudaErrorNotSupported)

@@ -44,6 +44,11 @@ struct PassArgs {
   const float2* tw_lo;   // W_N^a, a in [0,1024)           (forward sign; conjugated for SIGN=+1)
   const float2* tw_hi;   // W_N^(1024 b), b in [0, ceil(N/1024))
   const float2* tw_r;    // W_R^a, a in [0,R)
+  // Multi-GPU routing of the LAST pass (lean 160-point kernel only; null = plain store to `out`): every 128-byte output
+  // row (16 bins) goes to the ranks whose channels read it — route_mask[bin / 16] has one bit per rank — at the same
+  // offset inside that rank's spectrum allocation: (char*)(out + idx) + route_delta[rank]; route_delta[own rank] = 0.
+  const unsigned short* route_mask;
+  long long route_delta[16];
 };
 
 struct BigFftPlan {
@@ -71,6 +76,9 @@ struct BigFftIn {
   float scale = 1.f, gain = 1.f;
   int stat_from = 0;
   float* energy = nullptr;
+  // multi-GPU routing of the last pass (see PassArgs); honoured only when bigfft_can_route(plan)
+  const unsigned short* route_mask = nullptr;
+  long long route_delta[16] = {0};
 };
 // Executes `batch` transforms. tmp0/tmp1: scratch float2[batch][N] (tmp1 only needed when npass >= 3; for IN_C32 input
 // with npass >= 2 the input is NOT modified). sign: -1 forward, +1 backward (unnormalised).
@@ -79,6 +87,8 @@ int bigfft_exec(const BigFftPlan* plan, const BigFftIn& in, float2* out, long lo
 // preferred shared-memory carve-out (percent, or cudaSharedmemCarveoutMaxShared) of the lean pass kernels on the current
 // device: set it to the channel kernels' so that the two can share SMs (see bigfft_r128.cuh)
 void bigfft_set_carveout(int pct);
+// true if the plan's last pass is the lean 160-point kernel, which can store its output rows straight into peer memory
+bool bigfft_can_route(const BigFftPlan* plan);
 // number of kernel launches one bigfft_exec performs
 inline int bigfft_launches(const BigFftPlan* plan) { return plan->npass; }
 

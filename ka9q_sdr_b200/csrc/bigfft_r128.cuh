@@ -205,10 +205,26 @@ __global__ void __launch_bounds__(P160_THREADS, P160_MIN_CTAS) fft_pass160_last_
       for (int r = 0; r < 10; r++) v[r] = up[16 * r];
       Dft<10, -1>::run(v);
       float2* o = outb + (long long)ncols * q;
+      if (a.route_mask == nullptr) {
 #pragma unroll
-      for (int j = 0; j < 10; j++) o[(long long)ncols * 16 * j] = v[j];
+        for (int j = 0; j < 10; j++) o[(long long)ncols * 16 * j] = v[j];
+      } else {
+        // fused exchange: the 16 lanes of a half-warp hold one 128-byte row; it is stored into the spectrum buffer of
+        // every rank that reads it (peer memory over NVLink, own memory if this rank reads it) and nowhere else
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+          unsigned m = a.route_mask[(col0 + ncols * (q + 16 * j)) >> 4];
+          float2* dst = o + (long long)ncols * 16 * j;
+          while (m) {
+            const int r = __ffs(m) - 1;
+            m &= m - 1;
+            *reinterpret_cast<float2*>(reinterpret_cast<char*>(dst) + a.route_delta[r]) = v[j];
+          }
+        }
+      }
     }
   }
+  if (a.route_mask != nullptr) __threadfence_system();  // the peer stores are performed before the kernel ends
 }
 
 // Shared-memory carve-out of the lean pass kernels. CTAs of kernels with different carve-outs cannot be resident on one

@@ -27,6 +27,9 @@ constexpr int FFT2048_THREADS = 128;
 #ifndef FFT2048_TW_EARLY
 #define FFT2048_TW_EARLY 0
 #endif
+#ifndef FFT2048_TW_HALF
+#define FFT2048_TW_HALF 0
+#endif
 
 // Twiddle table layout (FFT2048_TW_FLOAT2 float2 entries, built by fft2048_fill_twiddles on the host), laid out so that
 // the lanes of a warp read CONSECUTIVE addresses (the L1 data pipe was the kernel's limiter, and a row per thread costs
@@ -63,6 +66,37 @@ __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb
                                         const float4* __restrict__ tw2s, bool war_sync = true) {
   const int t = threadIdx.x;
   // ---- stage 1: two radix-8 butterflies, p = t + 128e; y1[8p + j] = w_2048^(p j) * DFT8 ----
+#if FFT2048_TW_HALF
+  // Half the stage-1 twiddle loads: W_2048^((t+128) j) = W_2048^(t j) * W_16^j, so the second butterfly's outputs are first
+  // turned by the compile-time constants W_16^j and then share the first butterfly's seven table entries (one more
+  // rounding on those eight values; 56 fewer L1 wavefronts per transform).
+  {
+    Dft<8, SIGN>::run(&v[0]);
+    Dft<8, SIGN>::run(&v[8]);
+    const float4* A = reinterpret_cast<const float4*>(tw) + t;
+    const float h = 0.70710678118654752f, c1 = 0.92387953251128674f, s1 = 0.38268343236508977f;
+    // W_16^j = exp(-2 pi i j / 16) for the forward transform, conjugated for the backward one (tw_mul does that)
+    v[9] = tw_mul<SIGN>(v[9], c1, -s1);
+    v[10] = tw_mul<SIGN>(v[10], h, -h);
+    v[11] = tw_mul<SIGN>(v[11], s1, -c1);
+    v[12] = tw_mul<SIGN>(v[12], 0.f, -1.f);
+    v[13] = tw_mul<SIGN>(v[13], -s1, -c1);
+    v[14] = tw_mul<SIGN>(v[14], -h, -h);
+    v[15] = tw_mul<SIGN>(v[15], -c1, -s1);
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) {
+      const float4 w = __ldg(A + 256 * jj);
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        v[8 * e + 2 * jj + 1] = tw_mul<SIGN>(v[8 * e + 2 * jj + 1], w.x, w.y);
+        v[8 * e + 2 * jj + 2] = tw_mul<SIGN>(v[8 * e + 2 * jj + 2], w.z, w.w);
+      }
+    }
+    const float2 w7 = __ldg(tw + FFT2048_TW_B + t);
+    v[7] = tw_mul<SIGN>(v[7], w7.x, w7.y);
+    v[15] = tw_mul<SIGN>(v[15], w7.x, w7.y);
+  }
+#else
 #pragma unroll
   for (int e = 0; e < 2; e++) {
     const float4* A = reinterpret_cast<const float4*>(tw) + (t + 128 * e);
@@ -90,6 +124,7 @@ __device__ __forceinline__ void fft2048(float2 (&v)[16], float2* __restrict__ sb
 #endif
     v[8 * e + 7] = tw_mul<SIGN>(v[8 * e + 7], w7.x, w7.y);
   }
+#endif
   if (war_sync) __syncthreads();  // WAR: previous users of the buffer are done (CTA-uniform flag)
   {
     // a = 8p + j, swizzled a ^ (t & 15): only the low nibble changes, so per j one XOR on a 3-bit value

@@ -139,6 +139,9 @@ void mgpu_release(ka9q_stream* s) {
   if (s->d_mg_jobs) cudaFree(s->d_mg_jobs);
   if (s->d_mg_counter) cudaFree(s->d_mg_counter);
   if (s->d_mg_peer_flag_ptrs) cudaFree(s->d_mg_peer_flag_ptrs);
+  if (s->d_mg_mask) cudaFree(s->d_mg_mask);
+  s->d_mg_mask = nullptr;
+  s->mg_fused = false;
   s->d_flags = nullptr;
   s->d_mg_jobs = nullptr;
   s->d_mg_counter = nullptr;
@@ -247,8 +250,23 @@ int ka9q_stream_mgpu_setup(ka9q_stream* s, int transport, int rank, int nranks, 
     K9_CUDA(cudaMemcpy(s->d_mg_peer_flag_ptrs, fl.data(), sizeof(MgpuFlags*) * K9_MAX_RANKS, cudaMemcpyHostToDevice));
     K9_CUDA(cudaMalloc(&s->d_mg_counter, sizeof(unsigned)));
     K9_CUDA(cudaMemset(s->d_mg_counter, 0, sizeof(unsigned)));
-    // copy-job lists, one per spectrum buffer parity: (my blocks) x (peers) x (pieces of the peer's arc)
     K9_CHECK(s->cfg.max_blocks % nranks == 0, "max_blocks must be a multiple of the number of ranks");
+    // Fused form (default where the plan allows it, KA9Q_B200_MGPU_FUSED=0 keeps the copy kernel): the forward FFT's last
+    // pass stores each 128-byte output row straight into the spectrum buffer of every rank that reads it.
+    const char* ef = getenv("KA9Q_B200_MGPU_FUSED");
+    s->mg_fused = bigfft_can_route(&s->fwd) && !(ef && atoi(ef) == 0) && nranks <= 16;
+    K9_CHECK(!(s->mg_fused && s->n0_enabled), "the noise-density estimate needs the whole spectrum on every rank: not "
+                                               "available with the sharded exchange");
+    if (s->mg_fused) {
+      std::vector<unsigned short> mask((size_t)N / 16, 0);
+      for (int r = 0; r < nranks; r++)
+        for (const MgpuSeg& sg : s->mg_need[r])
+          for (long long tile = sg.lo / 16; tile < (sg.lo + sg.len) / 16; tile++) mask[(size_t)tile] |= (unsigned short)(1u << r);
+      K9_CUDA(cudaMalloc(&s->d_mg_mask, sizeof(unsigned short) * mask.size()));
+      K9_CUDA(cudaMemcpy(s->d_mg_mask, mask.data(), sizeof(unsigned short) * mask.size(), cudaMemcpyHostToDevice));
+      for (int r = 0; r < nranks; r++)
+        s->mg_delta[r] = (long long)((const char*)s->mg_peer_spec[r] - (const char*)s->d_spec);
+    }
   }
   return 0;
 }
@@ -385,8 +403,21 @@ int ka9q_stream_mgpu_compute(ka9q_stream* s, int nblocks, int resident) {
   }
   const int p = s->spec_wr;
   const int seq = ++s->mg_seq;
-  if (issue_fft(s, first_block, bf, cnt)) return -1;
-  if (G > 1) {
+  const bool fused = G > 1 && s->mg_transport == KA9Q_MGPU_P2P && s->mg_fused;
+  if (fused && seq > 2) {
+    // the last pass writes into the peers' buffer p: they must have finished reading it (two batches ago) first
+    K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_spec_free[p], 0));
+    mgpu_wait_kernel<<<1, 32, 0, s->s_fft>>>(s->d_flags, 1, p, G, me, seq - 2);
+  }
+  s->mg_route_now = fused;
+  const int fft_rc = issue_fft(s, first_block, bf, cnt);
+  s->mg_route_now = false;
+  if (fft_rc) return -1;
+  if (fused) {
+    TimedRegion tr(s, TC_BCAST, s->s_fft);
+    mgpu_signal_ready_kernel<<<1, 32, 0, s->s_fft>>>(s->d_mg_peer_flag_ptrs, G, me, p, seq);
+    K9_CHECK(cudaGetLastError() == cudaSuccess, "signal kernel launch failed");
+  } else if (G > 1) {
     TimedRegion tr(s, TC_BCAST, s->s_fft);
     if (s->mg_transport == KA9Q_MGPU_NCCL) {
       if (exchange_nccl(s, nblocks, p)) return -1;

@@ -706,6 +706,10 @@ int issue_fft(ka9q_stream* s, long long first_block, int blk_first, int blk_coun
   in.gain = s->cfg.gain_factor;
   in.stat_from = s->cfg.M - 1;
   in.energy = s->d_energy + blk_first;
+  if (s->mg_fused && s->mg_route_now) {  // channel-sharded multi-GPU: the last pass stores every row where it is read (mgpu.cu)
+    in.route_mask = s->d_mg_mask;
+    for (int r = 0; r < K9_MAX_RANKS; r++) in.route_delta[r] = s->mg_delta[r];
+  }
   K9_CUDA(cudaMemsetAsync(s->d_energy + blk_first, 0, sizeof(float) * blk_count, s->s_fft));
   K9_CUDA(cudaEventRecord(s->e_fft0, s->s_fft));
   {

@@ -120,6 +120,10 @@ struct ka9q_stream {
   unsigned* d_mg_counter = nullptr;                  // CTAs of the scatter kernel that have finished
   int mg_njobs = 0, mg_jobs_nblocks = 0;
   std::vector<CopyJob> mg_host_jobs[2];              // host copy of the job lists (copy-engine transport)
+  bool mg_route_now = false;                         // set by mgpu_compute around its issue_fft
+  bool mg_fused = false;                             // the forward FFT's last pass stores the arcs itself (no copy kernel)
+  unsigned short* d_mg_mask = nullptr;               // [N / 16] ranks that read each 16-bin row
+  long long mg_delta[K9_MAX_RANKS] = {};             // byte offset from this rank's spectrum allocation to each peer's
   int mg_wait_ready = 0;                             // sequence number the next channel launch has to wait for (P2P)
   MgpuFlags** d_mg_peer_flag_ptrs = nullptr;         // device copy of mg_peer_flags
   // live timing of the timed region (bench.py): event pairs around every forward FFT and every FM/AM/linear launch

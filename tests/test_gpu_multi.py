@@ -41,20 +41,37 @@ def _plan():
     return plan
 
 
+def _plan5():
+    """cfg5 geometry (N = 2 621 440 = 128 * 128 * 160: the plan whose last FFT pass can store into peer memory), 24 NBFM
+    channels spread over the band, both band edges and the wrap around array index 0 included"""
+    from ka9q_sdr_b200 import workloads
+    p = workloads.cfg5(8192)
+    sel = [0, 1, 2, 3, 1500, 1501, 3000, 3001, 4094, 4095, 4096, 4097, 4098, 5000, 5001, 6500, 6501, 7000, 7001, 8188, 8189,
+           8190, 8191, 2047]
+    p.channels = [p.channels[j] for j in sel]
+    p.name = "mgpu-test-cfg5"
+    return p
+
+
 _STIM = {}
 
 
 def _stimulus(plan, nb):
-    """generated once per session (time-domain synthesis of 26 carriers), handed to the rank processes through a file"""
-    if nb not in _STIM:
+    """generated once per session, handed to the rank processes through a file"""
+    key = (plan.name, nb)
+    if key not in _STIM:
         import tempfile
         from ka9q_sdr_b200 import synth
-        iq = synth.multi_channel(plan.samprate, nb, [c.bin for c in plan.channels], [c.mode for c in plan.channels],
-                                 plan.seed, plan.amplitude, plan.sigma)["iq"]
-        path = os.path.join(tempfile.gettempdir(), f"k9_mgpu_iq_{os.getpid()}_{nb}.npy")
+        if plan.N > 1000000:   # frequency-domain synthesis for the 61.44 MS/s geometry
+            iq = synth.comb_spectrum_iq(plan.samprate, nb, [c.bin for c in plan.channels], plan.seed, 0.02, plan.sigma,
+                                        deviation=plan.deviation)["iq"]
+        else:
+            iq = synth.multi_channel(plan.samprate, nb, [c.bin for c in plan.channels], [c.mode for c in plan.channels],
+                                     plan.seed, plan.amplitude, plan.sigma)["iq"]
+        path = os.path.join(tempfile.gettempdir(), f"k9_mgpu_iq_{os.getpid()}_{len(_STIM)}_{nb}.npy")
         np.save(path, iq)
-        _STIM[nb] = (iq, path)
-    return _STIM[nb]
+        _STIM[key] = (iq, path)
+    return _STIM[key]
 
 
 def _worker(rank, world, port, mode, q, iq_path):
@@ -65,17 +82,17 @@ def _worker(rank, world, port, mode, q, iq_path):
     from ka9q_sdr_b200 import channelizer as ch, mgpu, synth, workloads
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        plan = _plan()
+        plan = _plan5() if mode == "p2p-fused" else _plan()
         B, nbatch = 4, 2
         nb = B * nbatch
         iq = np.load(iq_path)
         mine = workloads.shard_contiguous(plan, rank, world)
         c = ch.Channelizer(plan.samprate, plan.L, plan.M, plan.D, device=rank, max_blocks=B)
         for s in mine:
-            c.add_channel(s.mode, s.bin)
+            c.add_channel(s.mode, s.bin, low=s.low, high=s.high)
         c.commit()
         pcm = np.empty((nb, c.pcm_stride), dtype=np.int16)
-        if mode in ("p2p", "nccl", "p2p-stream"):
+        if mode in ("p2p", "nccl", "p2p-stream", "p2p-fused"):
             mgpu.setup_sharded(c, rank, world, ch.MGPU_NCCL if mode == "nccl" else ch.MGPU_P2P)
         else:  # "bcast": rank 0 transforms, ncclBroadcast of the whole spectrum
             ids = [ch.nccl_unique_id() if rank == 0 else None]
@@ -89,7 +106,7 @@ def _worker(rank, world, port, mode, q, iq_path):
                 part = np.ascontiguousarray(iq[2 * a:2 * (a + n)])
                 c.push_at(part.ctypes.data_as(C.c_void_p), a, n)
                 c.mgpu_compute(B, resident=False)
-            elif mode in ("p2p", "nccl"):
+            elif mode in ("p2p", "nccl", "p2p-fused"):
                 c.push(blk.ctypes.data_as(C.c_void_p), B)
                 c.mgpu_compute(B, resident=True)
             else:
@@ -111,12 +128,12 @@ def _worker(rank, world, port, mode, q, iq_path):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("mode", ["p2p", "p2p-stream", "nccl", "bcast"])
+@pytest.mark.parametrize("mode", ["p2p", "p2p-stream", "p2p-fused", "nccl", "bcast"])
 def test_sharded_two_gpus_equal_one_gpu(mode):
     import torch.multiprocessing as mp
     from ka9q_sdr_b200 import channelizer as ch, synth
     world = 2
-    plan = _plan()
+    plan = _plan5() if mode == "p2p-fused" else _plan()
     B, nbatch = 4, 2
     nb = B * nbatch
     iq, iq_path = _stimulus(plan, nb)
@@ -133,7 +150,7 @@ def test_sharded_two_gpus_equal_one_gpu(mode):
     # single-GPU result of the whole plan
     c = ch.Channelizer(plan.samprate, plan.L, plan.M, plan.D, device=0, max_blocks=B)
     for s in plan.channels:
-        c.add_channel(s.mode, s.bin)
+        c.add_channel(s.mode, s.bin, low=s.low, high=s.high)
     c.commit()
     pcm, _ = c.run(iq, want_status=False)
     one = {(s.mode, s.bin): c.channel_pcm(pcm, i) for i, s in enumerate(plan.channels)}
