@@ -251,10 +251,15 @@ int ka9q_stream_mgpu_setup(ka9q_stream* s, int transport, int rank, int nranks, 
     K9_CUDA(cudaMalloc(&s->d_mg_counter, sizeof(unsigned)));
     K9_CUDA(cudaMemset(s->d_mg_counter, 0, sizeof(unsigned)));
     K9_CHECK(s->cfg.max_blocks % nranks == 0, "max_blocks must be a multiple of the number of ranks");
-    // Fused form (default where the plan allows it, KA9Q_B200_MGPU_FUSED=0 keeps the copy kernel): the forward FFT's last
-    // pass stores each 128-byte output row straight into the spectrum buffer of every rank that reads it.
+    // Three forms of the P2P exchange (all parity-tested, tests/test_gpu_multi.py):
+    //   pull  (default)               consumers LOAD their arcs out of the producers' spectrum buffers
+    //   push  (KA9Q_B200_MGPU_PULL=0) producers STORE the arcs into the consumers' buffers (copy kernel or copy engines)
+    //   fused (KA9Q_B200_MGPU_FUSED=1) the forward FFT's last pass stores each 128-byte output row straight into the
+    //                                 spectrum buffer of every rank that reads it (plans ending in the lean 160-point pass)
     const char* ef = getenv("KA9Q_B200_MGPU_FUSED");
-    s->mg_fused = bigfft_can_route(&s->fwd) && !(ef && atoi(ef) == 0) && nranks <= 16;
+    s->mg_fused = bigfft_can_route(&s->fwd) && ef && atoi(ef) != 0 && nranks <= 16;   // opt-in: measured slower
+    const char* ep = getenv("KA9Q_B200_MGPU_PULL");
+    s->mg_pull = !s->mg_fused && !(ep && atoi(ep) == 0);
     K9_CHECK(!(s->mg_fused && s->n0_enabled), "the noise-density estimate needs the whole spectrum on every rank: not "
                                                "available with the sharded exchange");
     if (s->mg_fused) {
@@ -325,6 +330,76 @@ static int exchange_nccl(ka9q_stream* s, int nblocks, int p) {
   const int r2 = p_ncclGroupEnd();
   if (r == 0) r = r2;
   K9_CHECK(r == 0, "NCCL sub-band exchange: %s", p_ncclGetErrorString ? p_ncclGetErrorString(r) : "error");
+  return 0;
+}
+
+// plain copy of a job list (used by the pull form; the push form's mgpu_scatter_kernel also raises the flags)
+__global__ void __launch_bounds__(SCATTER_THREADS) mgpu_gather_kernel(const CopyJob* __restrict__ jobs, int njobs) {
+  __shared__ CopyJob sj[32];
+  for (int j = threadIdx.x; j < njobs; j += blockDim.x) sj[j] = jobs[j];
+  __syncthreads();
+  const long long total = sj[njobs - 1].first + sj[njobs - 1].n16;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 8 * stride) {
+    int4 v[8];
+    int4* d[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const long long i = i0 + u * stride;
+      d[u] = nullptr;
+      if (i < total) {
+        int j = 0;
+        while (j + 1 < njobs && i >= sj[j + 1].first) j++;
+        // peer memory is read around the local L1 / L2 (ld.global.cg: nothing stale from two batches ago can be hit)
+        v[u] = __ldcg(sj[j].src + (i - sj[j].first));
+        d[u] = sj[j].dst + (i - sj[j].first);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (d[u]) *d[u] = v[u];
+  }
+}
+
+// Pull form: this rank loads its arcs of the peers' blocks out of the peers' spectrum buffers (NVLink peer LOADS run at
+// about twice the rate of SM-issued peer stores here). On the FFT stream, after this rank's own transform:
+//   ready[p][me] = seq on every peer -> wait for every peer's ready -> gather -> freed[p][me] = seq on every peer
+// (a producer may overwrite its buffer p two batches later only when every consumer has pulled: waited for before its FFT)
+static int exchange_pull(ka9q_stream* s, int nblocks, int p, int seq) {
+  const int G = s->mg_nranks, me = s->mg_rank, cnt = nblocks / G;
+  if (s->mg_jobs_nblocks != nblocks) {
+    std::vector<CopyJob> jobs[2];
+    for (int par = 0; par < 2; par++)
+      for (int peer = 0; peer < G; peer++) {
+        if (peer == me) continue;
+        for (int b = peer * cnt; b < (peer + 1) * cnt; b++)
+          for (const MgpuSeg& sg : s->mg_need[me]) {
+            const size_t off = ((size_t)par * s->cfg.max_blocks + b) * s->N + sg.lo;
+            const long long first = jobs[par].empty() ? 0 : jobs[par].back().first + jobs[par].back().n16;
+            jobs[par].push_back({(const int4*)(s->mg_peer_spec[peer] + off), (int4*)(s->d_spec + off), sg.len / 2, first});
+          }
+      }
+    K9_CHECK(jobs[0].size() <= 32, "too many exchange segments (max 32 per batch)");
+    s->mg_njobs = (int)jobs[0].size();
+    if (s->d_mg_jobs) cudaFree(s->d_mg_jobs);
+    s->d_mg_jobs = nullptr;
+    if (s->mg_njobs) {
+      K9_CUDA(cudaMalloc(&s->d_mg_jobs, sizeof(CopyJob) * 2 * s->mg_njobs));
+      K9_CUDA(cudaMemcpy(s->d_mg_jobs, jobs[0].data(), sizeof(CopyJob) * s->mg_njobs, cudaMemcpyHostToDevice));
+      K9_CUDA(cudaMemcpy((CopyJob*)s->d_mg_jobs + s->mg_njobs, jobs[1].data(), sizeof(CopyJob) * s->mg_njobs, cudaMemcpyHostToDevice));
+    }
+    s->mg_jobs_nblocks = nblocks;
+  }
+  static int ctas = 0;
+  if (!ctas) {
+    const char* e = getenv("KA9Q_B200_SCATTER_CTAS");
+    ctas = e && atoi(e) > 0 ? atoi(e) : 592;
+  }
+  mgpu_signal_ready_kernel<<<1, 32, 0, s->s_fft>>>(s->d_mg_peer_flag_ptrs, G, me, p, seq);
+  mgpu_wait_kernel<<<1, 32, 0, s->s_fft>>>(s->d_flags, 0, p, G, me, seq);
+  mgpu_gather_kernel<<<ctas, SCATTER_THREADS, 0, s->s_fft>>>((const CopyJob*)s->d_mg_jobs + (size_t)p * s->mg_njobs, s->mg_njobs);
+  mgpu_signal_free_kernel<<<1, 32, 0, s->s_fft>>>(s->d_mg_peer_flag_ptrs, G, me, p, seq);
+  K9_CHECK(cudaGetLastError() == cudaSuccess, "gather kernel launch failed");
   return 0;
 }
 
@@ -404,8 +479,10 @@ int ka9q_stream_mgpu_compute(ka9q_stream* s, int nblocks, int resident) {
   const int p = s->spec_wr;
   const int seq = ++s->mg_seq;
   const bool fused = G > 1 && s->mg_transport == KA9Q_MGPU_P2P && s->mg_fused;
-  if (fused && seq > 2) {
-    // the last pass writes into the peers' buffer p: they must have finished reading it (two batches ago) first
+  const bool pull = G > 1 && s->mg_transport == KA9Q_MGPU_P2P && s->mg_pull;
+  if ((fused || pull) && seq > 2) {
+    // fused: the last pass writes into the peers' buffer p, which they must have finished reading (two batches ago);
+    // pull: the transform overwrites this rank's buffer p, which every peer must have finished pulling from
     K9_CUDA(cudaStreamWaitEvent(s->s_fft, s->e_spec_free[p], 0));
     mgpu_wait_kernel<<<1, 32, 0, s->s_fft>>>(s->d_flags, 1, p, G, me, seq - 2);
   }
@@ -421,17 +498,19 @@ int ka9q_stream_mgpu_compute(ka9q_stream* s, int nblocks, int resident) {
     TimedRegion tr(s, TC_BCAST, s->s_fft);
     if (s->mg_transport == KA9Q_MGPU_NCCL) {
       if (exchange_nccl(s, nblocks, p)) return -1;
+    } else if (pull) {
+      if (exchange_pull(s, nblocks, p, seq)) return -1;
     } else {
       if (exchange_p2p(s, nblocks, p, seq)) return -1;
     }
   }
   if (publish_spectrum(s)) return -1;
-  if (G > 1 && s->mg_transport == KA9Q_MGPU_P2P) {
+  if (G > 1 && s->mg_transport == KA9Q_MGPU_P2P && !pull) {
     // the channel stream waits for every producer's arcs (issue_channels makes s_comp wait for e_spec_ready first)
     s->mg_wait_ready = seq;
   }
   if (issue_channels(s, nblocks)) return -1;
-  if (G > 1 && s->mg_transport == KA9Q_MGPU_P2P) {
+  if (G > 1 && s->mg_transport == KA9Q_MGPU_P2P && !pull) {
     mgpu_signal_free_kernel<<<1, 32, 0, s->s_comp>>>(s->d_mg_peer_flag_ptrs, G, me, p, seq);
     K9_CHECK(cudaGetLastError() == cudaSuccess, "signal kernel launch failed");
     // later FFTs into buffer p also wait for this signal having been sent (keeps seq order on the wire)

@@ -121,6 +121,7 @@ struct ka9q_stream {
   int mg_njobs = 0, mg_jobs_nblocks = 0;
   std::vector<CopyJob> mg_host_jobs[2];              // host copy of the job lists (copy-engine transport)
   bool mg_route_now = false;                         // set by mgpu_compute around its issue_fft
+  bool mg_pull = false;                              // consumers load their arcs from the producers' buffers (default)
   bool mg_fused = false;                             // the forward FFT's last pass stores the arcs itself (no copy kernel)
   unsigned short* d_mg_mask = nullptr;               // [N / 16] ranks that read each 16-bin row
   long long mg_delta[K9_MAX_RANKS] = {};             // byte offset from this rank's spectrum allocation to each peer's
