@@ -252,14 +252,15 @@ int ka9q_stream_mgpu_setup(ka9q_stream* s, int transport, int rank, int nranks, 
     K9_CUDA(cudaMemset(s->d_mg_counter, 0, sizeof(unsigned)));
     K9_CHECK(s->cfg.max_blocks % nranks == 0, "max_blocks must be a multiple of the number of ranks");
     // Three forms of the P2P exchange (all parity-tested, tests/test_gpu_multi.py):
-    //   pull  (default)               consumers LOAD their arcs out of the producers' spectrum buffers
-    //   push  (KA9Q_B200_MGPU_PULL=0) producers STORE the arcs into the consumers' buffers (copy kernel or copy engines)
+    //   push  (default)               producers STORE the arcs into the consumers' buffers (copy kernel, or the copy
+    //                                 engines with KA9Q_B200_MGPU_CE=1)
+    //   pull  (KA9Q_B200_MGPU_PULL=1) consumers LOAD their arcs out of the producers' spectrum buffers
     //   fused (KA9Q_B200_MGPU_FUSED=1) the forward FFT's last pass stores each 128-byte output row straight into the
     //                                 spectrum buffer of every rank that reads it (plans ending in the lean 160-point pass)
     const char* ef = getenv("KA9Q_B200_MGPU_FUSED");
     s->mg_fused = bigfft_can_route(&s->fwd) && ef && atoi(ef) != 0 && nranks <= 16;   // opt-in: measured slower
     const char* ep = getenv("KA9Q_B200_MGPU_PULL");
-    s->mg_pull = !s->mg_fused && !(ep && atoi(ep) == 0);
+    s->mg_pull = !s->mg_fused && ep && atoi(ep) != 0;                                   // opt-in: measured slower too
     K9_CHECK(!(s->mg_fused && s->n0_enabled), "the noise-density estimate needs the whole spectrum on every rank: not "
                                                "available with the sharded exchange");
     if (s->mg_fused) {
@@ -361,8 +362,8 @@ __global__ void __launch_bounds__(SCATTER_THREADS) mgpu_gather_kernel(const Copy
   }
 }
 
-// Pull form: this rank loads its arcs of the peers' blocks out of the peers' spectrum buffers (NVLink peer LOADS run at
-// about twice the rate of SM-issued peer stores here). On the FFT stream, after this rank's own transform:
+// Pull form: this rank loads its arcs of the peers' blocks out of the peers' spectrum buffers. On the FFT stream, after
+// this rank's own transform:
 //   ready[p][me] = seq on every peer -> wait for every peer's ready -> gather -> freed[p][me] = seq on every peer
 // (a producer may overwrite its buffer p two batches later only when every consumer has pulled: waited for before its FFT)
 static int exchange_pull(ka9q_stream* s, int nblocks, int p, int seq) {
