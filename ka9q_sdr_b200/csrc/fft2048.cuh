@@ -28,7 +28,7 @@ constexpr int FFT2048_THREADS = 128;
 #define FFT2048_TW_EARLY 0
 #endif
 #ifndef FFT2048_TW_HALF
-#define FFT2148_TW_HALF 0
+#define FFT2048_TW_HALF 1
 #endif
 
 // Twiddle table layout (FFT2048_TW_FLOAT2 float2 entries, built by fft2048_fill_twiddles on the host), laid out so that
