@@ -213,6 +213,15 @@ int ka9q_stream_add_channel(ka9q_stream *s, const ka9q_chan_params *p);
 int ka9q_stream_commit(ka9q_stream *s);
 /* Re-design one channel's filter after commit (the UI path: display.c:163-177). */
 int ka9q_stream_set_filter(ka9q_stream *s, int chan, float low, float high, float kaiser_beta);
+/* Off-grid carriers (the reference's second LO is any double: radio.c:217,299). The carrier of channel
+ * `chan` sits at (bin + fine_bins) * samprate / N, |fine_bins| <= 0.5. The grid part stays a bin rotation; the fraction
+ * becomes a phase ramp on the channel's impulse response (mixing before a filter h = filtering with h[m] e^{-j2 pi d m} and
+ * mixing afterwards) plus a rotation of the kept samples at the output rate (FM: ahead of the discriminator; linear:
+ * folded into the shift oscillator, radio.c:313; AM: the envelope does not see it). Call between add_channel and commit.
+ * ISB and pll / square channels are refused (grid only). ka9q_stream_split_carrier does the arithmetic:
+ * carrier_hz (from the first LO, either sign) -> nearest bin and the fraction left over. */
+int ka9q_stream_set_fine_lo(ka9q_stream *s, int chan, double fine_bins);
+int ka9q_stream_split_carrier(const ka9q_stream *s, double carrier_hz, long long *bin, double *fine_bins);
 
 /* PL-tone analyser (pltask, fm.c:189-285) for every de-emphasised FM channel: a /32 REAL slave of the audio master filter
  * feeding a 16384-point transform every 0.34 s. Enable before commit; the tone frequency (demod->sig.plfreq: 0 until the

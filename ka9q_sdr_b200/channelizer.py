@@ -88,6 +88,20 @@ class Channelizer:
         self.channels.append(int(p.channels) if m.demod_type == LINEAR_DEMOD else 1)
         return idx
 
+    def split_carrier(self, carrier_hz: float) -> tuple[int, float]:
+        """carrier (Hz from the first LO) -> (nearest grid bin, fraction of a bin left over)."""
+        b, f = C.c_longlong(0), C.c_double(0.0)
+        _lib.check(self.lib.ka9q_stream_split_carrier(self.h, float(carrier_hz), C.byref(b), C.byref(f)), "split_carrier")
+        return int(b.value), float(f.value)
+
+    def add_channel_hz(self, mode: str | Mode, carrier_hz: float, **kw) -> int:
+        """add_channel for a carrier anywhere in the band: grid bin + fine LO (ka9q_stream_set_fine_lo)."""
+        b, f = self.split_carrier(carrier_hz)
+        idx = self.add_channel(mode, b, **kw)
+        if f != 0.0:
+            _lib.check(self.lib.ka9q_stream_set_fine_lo(self.h, idx, f), "set_fine_lo")
+        return idx
+
     def enable_pl(self, enable: bool = True):
         """PL-tone analyser (fm.c:189-285) for the FM channels; call before commit. plfreq = status['reserved'][..., 1]."""
         _lib.check(self.lib.ka9q_stream_enable_pl(self.h, 1 if enable else 0), "enable_pl")

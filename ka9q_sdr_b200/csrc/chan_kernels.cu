@@ -395,6 +395,24 @@ __device__ __noinline__ void fm_discriminate_blanked(const float2* __restrict__ 
   *neg_out = neg;
 }
 
+// Off-grid carrier (ka9q_stream_set_fine_lo): rotate the kept samples by the fine part of the second LO,
+// exp(j 2 pi cyc n'), n' = output samples since stream start. The within-block part is applied here, in place; the phase
+// at the block's first sample is returned and joins the per-block LO phase. Cold, out of line.
+__device__ __noinline__ float2 fm_fine_rotate(float2* ybuf, int olen, double cyc, long long m) {
+  const float fc = (float)cyc;
+#pragma unroll 1
+  for (int o = threadIdx.x; o < olen; o += FFT2048_THREADS) {
+    float sn, cs;
+    sincospif(2.f * fc * (float)o, &sn, &cs);
+    ybuf[o] = cmul(ybuf[o], make_float2(cs, sn));
+  }
+  double base = cyc * (double)(m * olen);
+  base -= floor(base);
+  double sn, cs;
+  sincospi(2.0 * base, &sn, &cs);
+  return make_float2((float)cs, (float)sn);
+}
+
 // Squelch + discriminator for one channel-block whose kept samples (without the block's LO phase ph) are in sh.buf
 // (fm.c:86-160). Appends olen audio samples to the ring aud[] at rb, updates sh.S[h] and the status row. The discriminator only sees
 // phase differences, so ph enters once: the carried state conj(last good sample) is kept in the true (rotated) domain
@@ -407,6 +425,10 @@ __device__ __forceinline__ void fm_discriminate(const ChanLaunch& a, SH& sh, con
   const float2* ybuf = sh.buf + (NDEC - olen);  // kept samples y[0..olen)
   // (its barrier also publishes the kept samples store16_stats just wrote; red[] was last read a barrier ago)
   block_reduce3<2, !FM_FEWER_BARRIERS>(ssq, samp, minsq, sh.red);
+  if (sh.P[h].shift_cycles != 0.0) {  // FM: the field holds the fine LO of an off-grid carrier
+    ph = cmul(ph, fm_fine_rotate(sh.buf + (NDEC - olen), olen, sh.P[h].shift_cycles, a.block0 + b));
+    __syncthreads();
+  }
   if (a.filt_dbg) dump_filter_output(a.filt_dbg + ((long long)b * a.nchan_total + c) * olen, ybuf, olen, ph);
   const float bb_power = ssq / (2 * olen);
   const float avg_amp = samp / ((float)M_SQRT2 * olen);

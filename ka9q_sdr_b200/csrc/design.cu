@@ -80,10 +80,16 @@ __global__ void shift_window_kernel(const float2* __restrict__ h, const DesignSp
   const int wi = specs ? specs[c].window : fixed_window;
   const float* w = windows + (long long)wi * M;
   const float gain = 1. / N;
+  const float fine = specs ? specs[c].fine : 0.f;
   const float2* hc = h + (long long)c * N;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
     float2 v = make_float2(0.f, 0.f);
     if (n < M) v = shifted_value(hc, w, n, N, M, gain, real_only);
+    if (fine != 0.f && n < M) {  // h[n] * exp(+j 2 pi fine n): the filter an off-grid LO is equivalent to (stream.cu)
+      float sn, cs;
+      sincospif(2.f * fine * (float)n, &sn, &cs);
+      v = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+    }
     out[(long long)c * N + n] = v;
   }
 }

@@ -14,6 +14,7 @@ struct DesignSpec {
   float low, high;   // cycles/sample at the output rate, as passed to set_filter (filter.c:500)
   float gain;        // 1/N, times M_SQRT1_2 for REAL / CROSS_CONJ outputs (filter.c:518-522)
   int window;        // index into the window table
+  float fine;        // off-grid part of the carrier, cycles per output sample (bins / ndec): phase ramp on the impulse response
 };
 
 // Batched set_filter core for complex responses of length ndec (plan must be for ndec):

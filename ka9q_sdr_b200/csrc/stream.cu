@@ -82,13 +82,14 @@ static int design_channels(ka9q_stream* s, int first, int count) {
     normalised_edges(s, p, &all[i].low, &all[i].high);
     all[i].gain = response_gain(s, p);
     all[i].window = window_index(s, p.kaiser_beta);
+    all[i].fine = (float)(s->fine_bins[first + i] / NDEC);
   }
   // group identical specs: leader[i] = index (within the range) of the first channel with the same filter
   std::vector<int> leader(count), uniq;
   {
-    std::map<std::array<float, 4>, int> seen;
+    std::map<std::array<float, 5>, int> seen;
     for (int i = 0; i < count; i++) {
-      const std::array<float, 4> key = {all[i].low, all[i].high, all[i].gain, (float)all[i].window};
+      const std::array<float, 5> key = {all[i].low, all[i].high, all[i].gain, (float)all[i].window, all[i].fine};
       auto it = seen.find(key);
       if (it == seen.end()) {
         seen[key] = i;
@@ -262,7 +263,37 @@ int ka9q_stream_add_channel(ka9q_stream* s, const ka9q_chan_params* p) {
   q.bin %= s->N;
   if (q.bin < 0) q.bin += s->N;
   s->chans.push_back(q);
+  s->fine_bins.push_back(0.0);
   return (int)s->chans.size() - 1;
+}
+
+// Off-grid carriers. The second LO of the reference is any double (radio.c:217,299); the shared forward
+// FFT gives LOs on the N-point grid only. With f_LO = -(bin + e)/N: mixing before a filter h equals filtering with
+// h[m] * exp(+j 2 pi e m / N) and mixing afterwards, so the grid part stays a bin rotation, the
+// channel's impulse response is designed with that phase ramp (design.cu) and the kept samples are rotated by
+// exp(-j 2 pi e n / N), n = m L + D i, at the output rate: in the FM discriminator's input, folded into the shift
+// oscillator of the linear demodulator; the AM envelope does not see it. Not for ISB (the sideband fold does not commute
+// with the rotation) or the coherent modes (the loop tracks the residue itself; use the grid).
+int ka9q_stream_set_fine_lo(ka9q_stream* s, int chan, double bins) {
+  K9_CHECK(s, "null argument");
+  K9_CHECK(!s->committed, "ka9q_stream_set_fine_lo must be called before commit");
+  K9_CHECK(chan >= 0 && chan < (int)s->chans.size(), "bad channel");
+  K9_CHECK(bins >= -0.5 && bins <= 0.5, "the fine part of a carrier is at most half a bin");
+  const ka9q_chan_params& p = s->chans[chan];
+  K9_CHECK(bins == 0 || !(p.demod_type == KA9Q_LINEAR_DEMOD && (p.flags & (KA9Q_FLAG_ISB | KA9Q_FLAG_PLL))),
+           "ISB and coherent (pll / square) channels take carriers on the bin grid only");
+  s->fine_bins[chan] = bins;
+  return 0;
+}
+
+// carrier frequency (Hz from the first LO, either sign) -> nearest grid bin and the fraction left over
+int ka9q_stream_split_carrier(const ka9q_stream* s, double carrier_hz, long long* bin, double* fine_bins) {
+  K9_CHECK(s && bin && fine_bins, "null argument");
+  const double b = carrier_hz * (double)s->N / (double)s->cfg.samprate;
+  const double r = nearbyint(b);
+  *bin = (long long)r;
+  *fine_bins = b - r;
+  return 0;
 }
 
 static int commit_impl(ka9q_stream* s);
@@ -374,6 +405,7 @@ static int commit_impl(ka9q_stream* s) {
       // fm.c:86: (headroom * M_1_PI * dsamprate) / fabsf(low - high), evaluated in double, stored to float
       P.fm_gain = (p.headroom * M_1_PI * dsamprate) / fabsf(p.low - p.high);
       st[c].fm_state = make_float2(1.f, 0.f);  // fm.c:26
+      P.shift_cycles = -s->fine_bins[c] / NDEC;  // FM has no shift oscillator: the field carries the fine LO alone
       if (!(p.flags & KA9Q_FLAG_FLAT)) {
         int slot = -1;
         for (size_t i = 0; i < audio_betas.size(); i++)
@@ -397,6 +429,7 @@ static int commit_impl(ka9q_stream* s) {
         st[c].agc_gain = dB2voltage_f(100.0);  // linear.c:39
         // radio.c:313: shift * decimate / samprate, cycles per output sample
         P.shift_cycles = (p.shift == 0) ? 0.0 : (double)p.shift * s->cfg.decimate / (double)s->cfg.samprate;
+        P.shift_cycles -= s->fine_bins[c] / NDEC;  // the fine part of the second LO rides the same oscillator
         if (p.flags & KA9Q_FLAG_PLL) {
           // coherent modes: constants of linear.c:29-65 in the reference's own types and order of evaluation
           const bool square = p.flags & KA9Q_FLAG_SQUARE;

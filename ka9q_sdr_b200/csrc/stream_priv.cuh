@@ -48,6 +48,7 @@ struct ka9q_stream {
   float* d_energy = nullptr;
   float2* d_tw2048 = nullptr;
   std::vector<ka9q_chan_params> chans;
+  std::vector<double> fine_bins;  // off-grid part of each channel's carrier, in bins of the N-point grid, |.| <= 0.5
   std::vector<ChanParams> h_params;
   std::vector<float> h_noise_gain;
   ChanParams* d_params = nullptr;

@@ -336,3 +336,67 @@ def test_pl_tone_analyser_matches_reference(ref):
         else:
             assert np.isnan(got[-1, j]) and np.isnan(want[-1])
     c.close()
+
+
+def test_off_grid_carriers_fine_lo(ref):
+    """carriers BETWEEN the bins of the shared forward FFT (12.5 / 25 kHz rasters are not on the 23.4375 Hz
+    grid). The reference mixes with any double (radio.c:217,299) ahead of its own FFT; here the grid part is a bin rotation,
+    the fraction a phase ramp on the impulse response plus a rotation at the output rate (ka9q_stream_set_fine_lo). Same
+    tolerances as the on-grid parity tests: filter output 1e-5 relative RMS, PCM +-1 LSB. Fractions of both signs, the
+    half-bin edge, an FM pair whose partner is on the grid, stereo IQ, and CW with its 700 Hz shift oscillator on top."""
+    fs = 192000
+    D, L, M, N = synth.geometry(fs)
+    nb = 30
+    n = nb * L
+    rng = np.random.default_rng(44)
+    hz = fs / N
+    f_fm1, f_fm2, f_fm3 = 1024.37 * hz, -2304.5 * hz, 2600 * hz          # 0.37, the -0.5 edge, on the grid
+    f_am, f_usb, f_cw, f_iq = -1024.21 * hz, 511.68 * hz, -320.45 * hz, 120.13 * hz
+    x = (synth.fm_carrier(n, fs, f_fm1, 1000.0, 3000.0, 0.15)
+         + synth.fm_carrier(n, fs, f_fm2, 700.0, 2500.0, 0.15)
+         + synth.fm_carrier(n, fs, f_fm3, 400.0, 2000.0, 0.15)
+         + synth.am_carrier(n, fs, f_am, 1000.0, 0.5, 0.1)
+         + synth.ssb_two_tone(n, fs, f_usb, [700.0, 1900.0], [0.05, 0.05])
+         + synth.ssb_two_tone(n, fs, f_cw, [40.0], [0.08])
+         + synth.ssb_two_tone(n, fs, f_iq, [-2100.0, 900.0], [0.04, 0.06])
+         + synth.awgn(rng, n, 0.005))
+    iq = synth._quantize(x)
+    chans = [("FM", f_fm1), ("AM", f_am), ("USB", f_usb), ("FM", f_fm2), ("CWU", f_cw), ("FM", f_fm3), ("IQ", f_iq)]
+    c = ch.Channelizer(fs, L, M, D, max_blocks=4, capture_filter_output=True)
+    fines = []
+    for mode, f in chans:
+        i = c.add_channel_hz(mode, f)
+        b, fr = c.split_carrier(f)
+        assert abs((b + fr) * hz - f) < 1e-6 and abs(fr) <= 0.5
+        fines.append(fr)
+    assert abs(fines[0] - 0.37) < 1e-6 and abs(abs(fines[3]) - 0.5) < 1e-6 and abs(fines[5]) < 1e-9
+    c.commit()
+    pcm = np.empty((nb, c.pcm_stride), dtype=np.int16)
+    filt = [[] for _ in chans]
+    sts = []
+    for b0 in range(0, nb, 4):
+        k = min(4, nb - b0)
+        _, st = c.process(iq[2 * b0 * L:2 * (b0 + k) * L], pcm[b0:b0 + k])
+        sts.append(st)
+        for i in range(len(chans)):
+            filt[i].append(c.filter_output(i, k))
+    st = np.concatenate(sts)
+    for i, (mode, f) in enumerate(chans):
+        r = ref.chain_run(mode, fs, L, M, D, iq, carrier_hz=f, want_filt=True)       # LO2 = -f, an arbitrary double
+        check_pcm(mode, c.channel_pcm(pcm, i), r.pcm, L // D, label=f"{mode}@{f:.2f}Hz ")
+        got = np.concatenate(filt[i])
+        if mode == "FM":          # the capture is taken after the rotation: the complex samples themselves must agree
+            assert rel_rms(got, r.filt[:nb]) < FILT_TOL, (mode, rel_rms(got, r.filt[:nb]))
+            assert np.all(st["squelch_open"][2:, i] == 1)
+            np.testing.assert_allclose(st["foffset"][2:, i], r.status["foffset"][2:nb], atol=0.05)
+        elif mode == "AM":        # the envelope detector needs no rotation: magnitudes
+            assert rel_rms(np.abs(got), np.abs(r.filt[:nb])) < FILT_TOL
+    # and the feature is refused where it cannot be exact
+    c2 = ch.Channelizer(fs, L, M, D, max_blocks=1)
+    for mode in ("ISB", "CAM"):
+        j = c2.add_channel(mode, 100)
+        assert c2.lib.ka9q_stream_set_fine_lo(c2.h, j, 0.25) != 0
+        assert c2.lib.ka9q_stream_set_fine_lo(c2.h, j, 0.0) == 0
+    assert c2.lib.ka9q_stream_set_fine_lo(c2.h, 0, 0.75) != 0
+    c2.close()
+    c.close()
