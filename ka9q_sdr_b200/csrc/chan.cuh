@@ -111,6 +111,9 @@ struct ChanLaunch {
   // work list for this launch
   const int2* work;          // FM: (chanA, chanB or -1); AM / linear: (chan, -1)
   int nwork;
+  // FM block-split form (chan_kernels.cu: fm_split_wait): per-pair count of discriminated blocks; CTAs per pair
+  long long* fm_seq;         // [nwork] or null (then never split)
+  int fm_split;              // set by launch_fm
   // AM / linear scratch between the front, recurrence and output kernels (rows indexed by block*nwork + work index)
   float* agc_x;              // [nblocks*nwork][olen]: amplitude in; AM: (s - DC)*gain out, linear: gain out
   float2* agc_y;             // [nblocks*nwork][olen]: kept filter output (linear only)

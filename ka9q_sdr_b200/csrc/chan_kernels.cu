@@ -536,20 +536,70 @@ __device__ __noinline__ void fm_flat_output(const float* audA, const float* audB
   }
 }
 
+// ---- block-split form (few pairs per GPU) ----
+// A cluster of `fm_split` CTAs shares one pair: CTA e takes blocks b = e (mod split). The transforms of different blocks
+// are independent; what chains the blocks of a channel is small: the discriminator / squelch state (ChanState) and the
+// audio ring. So block b's CTA runs its first predetection transform at once, then waits until block b-1's CTA has (1)
+// finished both discriminators and (2) loaded its own 2048-sample audio window out of the ring (block b's audio
+// overwrites the oldest part of that window). State travels through a.state[], the order through one sequence number
+// per pair (absolute block count, release / acquire at GPU scope). The cluster guarantees that the CTAs are co-resident.
+// want: blocks of this pair discriminated since stream start, as the block about to be discriminated needs it
+__device__ __noinline__ void fm_split_wait(const long long* f, const ChanState* state, long long want, FmShared& sh, int2 wk) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    const long long t0 = clock64();
+    while (true) {
+      long long v;
+      asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= want) break;
+      __nanosleep(40);
+      if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s: the partner CTA is gone; fail loudly instead of hanging
+    }
+  }
+  __syncthreads();
+  if (t < 2) {
+    const int c = t ? wk.y : wk.x;
+    if (c >= 0) {
+      const int* src = reinterpret_cast<const int*>(state + c);
+      int* dst = reinterpret_cast<int*>(&sh.S[t]);
+#pragma unroll
+      for (int i = 0; i < (int)(sizeof(ChanState) / sizeof(int)); i++) dst[i] = __ldcg(src + i);
+    }
+  }
+  __syncthreads();
+}
+__device__ __noinline__ void fm_split_signal(long long* f, ChanState* state, long long done, FmShared& sh, int2 wk) {
+  const int t = threadIdx.x;
+  if (t < 2) {
+    const int c = t ? wk.y : wk.x;
+    if (c >= 0) state[c] = sh.S[t];
+  }
+  __syncthreads();  // every thread's ring loads and the two state rows are ordered before the release below
+  if (t == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s64 [%0], %1;" ::"l"(f), "l"(done) : "memory");
+  }
+}
+
 // OLEN_T: output samples per block known at compile time (960 = the reference geometry at every input rate, SURVEY
 // Appendix B) so the kept-row tests fold away; 0 = take it from the launch arguments.
-template <int OLEN_T>
+template <int OLEN_T, bool SPLIT>
 __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(const ChanLaunch a) {
   __shared__ FmShared sh;
   const int t = threadIdx.x;
-  const int2 wk = a.work[blockIdx.x];
+  const int split = SPLIT ? a.fm_split : 1;          // CTAs per pair (= cluster size)
+  const int pairi = SPLIT ? blockIdx.x / split : blockIdx.x;
+  const int e0 = SPLIT ? blockIdx.x % split : 0;     // this CTA's first block
+  const int2 wk = a.work[pairi];
   fft2048_stage_tw2(sh.tw2, a.tw2048);
   if (t < 2) {
     const int c = t ? wk.y : wk.x;
     if (c >= 0) {
       sh.P[t] = a.params[c];
       sh.S[t] = a.state[c];
-      sh.ephase[t] = phase_index0(sh.P[t].bin, a.start0, a.N);
+      int ep = phase_index0(sh.P[t].bin, a.start0, a.N);
+      for (int i = 0; i < e0; i++) ep = phase_advance(ep, sh.P[t].phase_step, a.N);
+      sh.ephase[t] = ep;
     }
   }
 #if FM_TMA
@@ -575,7 +625,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
   float* const histB = a.audio_hist + (long long)(wk.y >= 0 ? wk.y : a.nchan_total) * NDEC;
   float2 v[16];
 
-  for (int b = 0; b < a.nblocks; b++) {
+  for (int b = e0; b < a.nblocks; b += split) {
     const long long m = a.block0 + b;
     const float2* X = a.spec + (long long)b * a.spec_stride;
     int16_t* pcm_row = a.pcm + (long long)b * a.pcm_stride;
@@ -614,7 +664,10 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
 #endif
           load_filtered16(v, X, a.N, (int)sh.P[h].bin, a.resp + (long long)sh.P[h].resp_slot * NDEC);
       } else if (job == 2) {
-        if (!filtered) break;
+        if (!filtered) {
+          if (SPLIT) fm_split_signal(a.fm_seq + pairi, a.state, m + 1, sh, wk);
+          break;
+        }
         // Two real channels ride one complex transform, z = audA + j audB (the filter's impulse response is real),
         // straight into the transform's input registers: row j = e + 2r of thread t is sample p = t + 128j. The
         // discriminators appended this block's samples to the rings (global memory, made visible to the CTA by the
@@ -625,8 +678,10 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
 #pragma unroll
           for (int r = 0; r < 8; r++) {
             const int ri = (r0 + 128 * (e + 2 * r)) & (NDEC - 1);
-            v[8 * e + r] = make_float2(histA[ri], -histB[ri]);
+            // (block-split form: the older part of the window was written by another CTA, so no L1)
+            v[8 * e + r] = SPLIT ? make_float2(__ldcg(histA + ri), -__ldcg(histB + ri)) : make_float2(histA[ri], -histB[ri]);
           }
+        if (SPLIT) fm_split_signal(a.fm_seq + pairi, a.state, m + 1, sh, wk);  // the next block's discriminators may overwrite the ring now
       }
       // the buffer's previous readers are a barrier behind us except after job 2 (its last stage just read it)
       fft2048<+1>(v, sh.buf, a.tw2048, sh.tw2, !FM_FEWER_BARRIERS || job == 3 || (FM_TMA == 1 && job < 2));
@@ -635,12 +690,17 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
         const int e = sh.ephase[h];
         __syncthreads();  // every thread has read its stage-3 inputs; the buffer can take the output
         store16_stats(v, sh.buf, first, &ssq, &samp, &minsq);
+        if (SPLIT && job == 0 && b > 0) fm_split_wait(a.fm_seq + pairi, a.state, m, sh, wk);  // block b-1's state and ring are final
         fm_discriminate(a, sh, olen, h, c, b, ssq, samp, minsq, phase_from_index(a, e), h ? histB : histA,
                         (ringbase + first) & (NDEC - 1));
-        if (t == 0) sh.ephase[h] = phase_advance(e, sh.P[h].phase_step, a.N);
+        if (t == 0) {
+          int ep = e;
+          for (int i = 0; i < split; i++) ep = phase_advance(ep, sh.P[h].phase_step, a.N);
+          sh.ephase[h] = ep;
+        }
       } else if (job == 2) {
         if (a.pl_spec) {  // PL-tone analyser enabled: the low bins of Z = FFT(audA + j audB) for pl_kernel (Z = conj(v))
-          float2* o = a.pl_spec + ((long long)b * a.pl_npairs + blockIdx.x) * 65;
+          float2* o = a.pl_spec + ((long long)b * a.pl_npairs + pairi) * 65;
           if (t <= 32) o[t] = make_float2(v[0].x, -v[0].y);
           if (t >= 96) o[33 + 127 - t] = make_float2(v[15].x, -v[15].y);  // Z[2048 - k], k = 128 - t
         }
@@ -672,7 +732,7 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
                      wk.y >= 0 ? pcm_row + sh.P[1].pcm_off : nullptr, olen);
     __syncthreads();
   }
-  if (t < 2) {
+  if (!SPLIT && t < 2) {  // (block-split form: the CTA of the last block stored the state when it signalled)
     const int c = t ? wk.y : wk.x;
     if (c >= 0) a.state[c] = sh.S[t];
   }
@@ -1400,15 +1460,49 @@ int launch_fm(const ChanLaunch& a, cudaStream_t st, bool mixed) {
   cudaGetDevice(&dev);
   dev &= 63;
   if (configured[dev] != pct + 1000) {
-    cudaFuncSetAttribute(fm_kernel<960>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fm_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fm_kernel<960, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fm_kernel<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fm_kernel<960, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fm_kernel<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     configured[dev] = pct + 1000;
   }
-  if (a.olen == 960)
-    fm_kernel<960><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
-  else
-    fm_kernel<0><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  // Few pairs: split every pair's blocks over a cluster of 2 (or 4) CTAs (fm_split_wait).
+  static int sms[64];
+  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  const char* ev = getenv("KA9Q_B200_FM_SPLIT");  // 1 / 2 / 4 force the form (tests, A/B); read per launch
+  const int forced = ev ? atoi(ev) : -1;
+  // Measured (scripts/gpu_fm_split_probe.py, cfg5 stream, 8 blocks): 32 pairs 0.0625 -> 0.0534 ms with 2 CTAs per pair,
+  // 0.0529 with 4; 256 pairs 0.1065 -> 0.1043 / 0.1137; 512 pairs 0.1352 -> 0.1330 / 0.1689. The blocks of a pair stay
+  // chained through both discriminators and the ring loads (more than half of a pair-block at single-CTA latency), so
+  // the form pays only while most SMs would otherwise hold one CTA or none: 2 CTAs per pair up to two pairs per SM.
+  int split = 1;
+  if (a.fm_seq && a.nblocks >= 2) {
+    if (a.nwork <= 2 * sms[dev]) split = 2;
+    if (forced == 1 || forced == 2 || (forced == 4 && a.nblocks >= 4)) split = forced;
+  }
+  if (split == 1) {
+    if (a.olen == 960)
+      fm_kernel<960, false><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
+    else
+      fm_kernel<0, false><<<a.nwork, FFT2048_THREADS, 0, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
+  ChanLaunch as = a;
+  as.fm_split = split;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.nwork * split);
+  cfg.blockDim = dim3(FFT2048_THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = split;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const cudaError_t e = a.olen == 960 ? cudaLaunchKernelEx(&cfg, fm_kernel<960, true>, as)
+                                      : cudaLaunchKernelEx(&cfg, fm_kernel<0, true>, as);
+  return e == cudaSuccess ? 0 : -1;
 }
 template <bool LINEAR, int G>
 static int launch_agc_g(const ChanLaunch& a, cudaStream_t st) {

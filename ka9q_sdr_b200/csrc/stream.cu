@@ -480,6 +480,10 @@ static int commit_impl(ka9q_stream* s) {
   if (upload_work(w_fm, &s->d_work_fm) || upload_work(w_am, &s->d_work_am) || upload_work(w_lin, &s->d_work_lin) ||
       upload_work(w_pll, &s->d_work_pll))
     return -1;
+  if (s->n_fm) {  // block-split form of the FM kernel: one sequence number per pair
+    K9_CUDA(cudaMalloc(&s->d_fm_seq, sizeof(long long) * s->n_fm));
+    K9_CUDA(cudaMemset(s->d_fm_seq, 0, sizeof(long long) * s->n_fm));
+  }
   if (s->n_pll) {
     K9_CUDA(cudaStreamCreateWithFlags(&s->s_pll, cudaStreamNonBlocking));
     K9_CUDA(cudaEventCreateWithFlags(&s->e_pll, cudaEventDisableTiming));
@@ -831,6 +835,7 @@ int issue_channels(ka9q_stream* s, int nblocks) {
   if (s->n_fm) {
     a.work = s->d_work_fm;
     a.nwork = s->n_fm;
+    a.fm_seq = s->d_fm_seq;
     if (s->n_pl) {
       a.pl_spec = s->d_pl_spec;
       a.pl_npairs = s->n_fm;
@@ -1065,7 +1070,8 @@ static void release_resources(ka9q_stream* s) {
                   (void**)&s->d_pl_spec, (void**)&s->d_pl_resp, (void**)&s->d_pl_work, (void**)&s->d_pl_state, (void**)&s->d_pl_ring,
                   (void**)&s->d_work_pll, (void**)&s->d_pll_params, (void**)&s->d_pll_state, (void**)&s->d_pll_ring,
                   (void**)&s->d_n0_chan, (void**)&s->d_n0_P, (void**)&s->d_n0_T, (void**)&s->d_n0_list, (void**)&s->d_n0_raw,
-                  (void**)&s->d_n0_smooth, (void**)&s->d_n0_state, (void**)&s->d_n0_partial, (void**)&s->d_n0_blk};
+                  (void**)&s->d_n0_smooth, (void**)&s->d_n0_state, (void**)&s->d_n0_partial, (void**)&s->d_n0_blk,
+                  (void**)&s->d_fm_seq};
   for (void** p : dev) {
     if (*p) cudaFree(*p);
     *p = nullptr;

@@ -66,6 +66,7 @@ struct ka9q_stream {
   float2* d_filt = nullptr;
   float* d_windows = nullptr;
   std::vector<float> betas;  // distinct Kaiser betas -> window table rows
+  long long* d_fm_seq = nullptr;  // FM block-split form: discriminated blocks per pair
   int2 *d_work_fm = nullptr, *d_work_am = nullptr, *d_work_lin = nullptr, *d_work_pll = nullptr;
   int n_fm = 0, n_am = 0, n_lin = 0, n_pll = 0;
   PllParams* d_pll_params = nullptr;

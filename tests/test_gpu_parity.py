@@ -231,6 +231,51 @@ def test_split_and_fused_agc_kernels_are_bit_identical(monkeypatch):
         assert np.abs(res["0"][0]).max() > 1000
 
 
+def test_fm_block_split_form_is_bit_identical(monkeypatch):
+    """With few FM pairs per GPU the FM kernel splits every pair's blocks over a cluster of 2 or 4 CTAs (launch_fm,
+    fm_split_wait: state and ring order handed from block to block through global memory). PCM, status and the state
+    carried into later batches must equal the one-CTA-per-pair form bit for bit: carriers that drop in and out (squelch
+    state machine, the carried discriminator state), a weak carrier (threshold-extension blanking), an odd channel count
+    (a pair without partner), FLAT channels (no audio filter), batches of 7, 5 and 1 blocks."""
+    fs, D, L, M, N = 192000, 4, 3840, 4353, 8192
+    nb = 27
+    n = nb * L
+    rng = np.random.default_rng(77)
+    t = np.arange(n) / fs
+    x = synth.awgn(rng, n, 0.01)
+    chans = []
+    for i in range(9):
+        k = -3200 + 800 * i
+        gate = ((t * (3 + i)) % 1.0) < (0.55 + 0.04 * i) if i % 3 == 0 else 1.0     # every third carrier keys on and off
+        amp = 0.012 if i == 4 else 0.08                                              # one near the FM threshold
+        x = x + gate * synth.fm_carrier(n, fs, k * fs / N, 300.0 + 100 * i, 2500.0, amp)
+        chans.append(("FMF" if i in (2, 7) else "FM", k, {}))
+    cfg = dict(samprate=fs, D=D, L=L, M=M, N=N, iq=synth._quantize(x))
+    res = {}
+    for split in ("1", "2", "4"):
+        monkeypatch.setenv("KA9Q_B200_FM_SPLIT", split)
+        out = []
+        for mb in (7, 5, 1):
+            c, pcm, st, filt = run_gpu(cfg, chans, nb, max_blocks=mb, capture=False)
+            out.append((pcm.copy(), st.copy()))
+            c.close()
+        res[split] = out
+    monkeypatch.delenv("KA9Q_B200_FM_SPLIT")
+    c, pcm, st, filt = run_gpu(cfg, chans, nb, max_blocks=7, capture=False)          # the launcher's own choice
+    res["auto"] = [(pcm.copy(), st.copy())]
+    c.close()
+    ref_pcm, ref_st = res["1"][0]
+    assert np.abs(ref_pcm).max() > 1000
+    opened = ref_st["squelch_open"]
+    assert opened[:, 0].min() == 0 and opened[:, 0].max() == 1                       # the squelch really moved
+    assert (ref_st["reserved"][:, 4, 0] == 0).any()                                  # the blanking path really ran
+    for key, outs in res.items():
+        for j, (p, s_) in enumerate(outs):
+            assert np.array_equal(p, ref_pcm), (key, j)
+            for f in ("bb_power", "snr", "foffset", "pdeviation", "squelch_open", "reserved"):
+                assert np.array_equal(s_[f], ref_st[f], equal_nan=True), (key, j, f)
+
+
 def test_fm_squelch_closes_on_noise_like_the_reference(ref):
     cfg = synth.cfg1_fm(12)
     rng = np.random.default_rng(9)
