@@ -481,10 +481,20 @@ def run_ours(args, plan):
     for _ in range(args.warmup + n_extra):
         step_resident()
     barrier()
-    c.timer_start()
+    # the headline interval carries no per-kernel event records (they cost microseconds per step); the per-class times
+    # come from the serialised pass below
+    c.timer_start(regions=bool(args.timeline))
     for _ in range(args.steps):
         step_resident()
     ms_total, _ = c.timer_stop()
+    if args.timeline:
+        # where the step's time goes when everything overlaps: the bracketed regions of the last steps of the timed
+        # interval, per rank (start = the region's stream reached it, end = its kernels finished)
+        tl = c.timer_timeline()
+        last = [r for r in tl if r[1] >= ms_total - 8 * ms_total / args.steps]
+        with open(f"{args.timeline}.rank{rank}.json", "w") as f:
+            json.dump({"rank": rank, "ms_per_step": ms_total / args.steps, "t_end_ms": ms_total,
+                       "regions": [[n, round(a, 4), round(b, 4)] for n, a, b in last]}, f)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel durations for the roofline: same steps with the FFT/channel overlap switched off, so every event pair
@@ -583,7 +593,7 @@ def run_ours(args, plan):
         cw.sync()
         if multi:
             dist.barrier()
-        cw.timer_start()
+        cw.timer_start(regions=False)
         for _ in range(args.steps):
             cw.compute_resident(Bw)
         msw, _ = cw.timer_stop()
@@ -727,6 +737,7 @@ def main():
                          "plan on its own FFT (weak, no coupling); allgather / broadcast = full-plan ranks with the "
                          "spectrum all-gathered / broadcast by NCCL")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="sharded mode: exchange transport")
+    ap.add_argument("--timeline", default=None, help="write the per-region timeline of the last timed steps to FILE.rankR.json")
     ap.add_argument("--no-weak", dest="weak", action="store_false", help="skip the weak-scaling line of multi-GPU runs")
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="skip the other workloads (AM / USB at scale, cfg4, front-end service) of the N = 1 run")

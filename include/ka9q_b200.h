@@ -277,7 +277,12 @@ int ka9q_stream_last_timing(ka9q_stream *s, float *total_ms, float *fft_ms, floa
 /* 1 (default): the forward FFT of batch k+1 overlaps the channel kernels of batch k; 0: serialised (per-kernel timing) */
 int ka9q_stream_set_overlap(ka9q_stream *s, int enable);
 int ka9q_stream_timer_start(ka9q_stream *s);
+/* as timer_start, but only the outer event pair is recorded (no per-kernel events inside the timed steps) */
+int ka9q_stream_timer_start_plain(ka9q_stream *s);
 int ka9q_stream_timer_stop(ka9q_stream *s, float *ms_total, float *class_ms, int *class_launches);
+/* After timer_stop: the bracketed regions in issue order as (class, start, end), ms from timer_start; class 5 = waiting
+ * for peer flags (multi-GPU). Returns the number of regions written (<= max_regions). */
+int ka9q_stream_timer_timeline(ka9q_stream *s, int max_regions, int *cls, float *start_ms, float *end_ms);
 
 /* Multi-GPU: channels are sharded by the caller (each rank adds only its own channels); the rank that owns the
  * I/Q input runs the forward FFT and broadcasts the spectrum. The caller supplies the broadcast as a callback

@@ -78,7 +78,7 @@ EXPORTED = [
     "ka9q_rtp_process", "ka9q_pcm_packetise", "ka9q_stream_wait_fetched", "ka9q_status_encode_signals",
     "ka9q_stream_needed_bins", "ka9q_stream_mgpu_export", "ka9q_stream_mgpu_setup", "ka9q_stream_mgpu_input_range",
     "ka9q_stream_push_at", "ka9q_stream_mgpu_compute", "ka9q_stream_mgpu_error", "ka9q_stream_blocks_done",
-    "ka9q_stream_enable_n0", "ka9q_stream_fetch_n0", "ka9q_stream_enable_pl", "ka9q_stream_set_fine_lo", "ka9q_stream_split_carrier", "ka9q_frontend_create", "ka9q_frontend_destroy",
+    "ka9q_stream_enable_n0", "ka9q_stream_fetch_n0", "ka9q_stream_enable_pl", "ka9q_stream_timer_timeline", "ka9q_stream_timer_start_plain", "ka9q_stream_set_fine_lo", "ka9q_stream_split_carrier", "ka9q_frontend_create", "ka9q_frontend_destroy",
     "ka9q_frontend_process", "ka9q_frontend_process_to_stream", "ka9q_frontend_rerun_resident",
     "ka9q_frontend_set_estimates", "ka9q_frontend_get_status", "ka9q_stream_push_device",
     "ka9q_stream_sync_input", "ka9q_rx_create", "ka9q_rx_destroy", "ka9q_rx_inject", "ka9q_rx_drain", "ka9q_rx_start", "ka9q_rx_stop",
@@ -172,6 +172,8 @@ def lib():
     L.ka9q_rx_get_stats.restype = None
     L.ka9q_pcm_send_block.argtypes = [ci, vp, vp, vp, vp, ci, ci, ci]
     L.ka9q_stream_enable_pl.argtypes = [vp, ci]
+    L.ka9q_stream_timer_timeline.argtypes = [vp, ci, vp, vp, vp]
+    L.ka9q_stream_timer_start_plain.argtypes = [vp]
     L.ka9q_stream_set_fine_lo.argtypes = [vp, ci, C.c_double]
     L.ka9q_stream_split_carrier.argtypes = [vp, C.c_double, vp, vp]
     L.ka9q_stream_enable_n0.argtypes = [vp, ci]

@@ -206,8 +206,12 @@ class Channelizer:
     def set_overlap(self, enable: bool):
         _lib.check(self.lib.ka9q_stream_set_overlap(self.h, 1 if enable else 0), "set_overlap")
 
-    def timer_start(self):
-        _lib.check(self.lib.ka9q_stream_timer_start(self.h), "timer_start")
+    def timer_start(self, regions: bool = True):
+        """regions=False: only the outer event pair (no per-kernel event records inside the timed steps)."""
+        if regions:
+            _lib.check(self.lib.ka9q_stream_timer_start(self.h), "timer_start")
+        else:
+            _lib.check(self.lib.ka9q_stream_timer_start_plain(self.h), "timer_start_plain")
 
     def timer_stop(self):
         """Returns (region_ms, {class: (ms, launches)}) for classes fft, fm, am, linear, bcast."""
@@ -217,6 +221,15 @@ class Channelizer:
         _lib.check(self.lib.ka9q_stream_timer_stop(self.h, C.byref(ms), cms, cl), "timer_stop")
         names = ("fft", "fm", "am", "linear", "bcast")
         return ms.value, {n: (cms[i], cl[i]) for i, n in enumerate(names)}
+
+    def timer_timeline(self, max_regions: int = 4096):
+        """After timer_stop: [(class name, start ms, end ms)] of the bracketed regions, in issue order."""
+        cls = (C.c_int * max_regions)()
+        t0 = (C.c_float * max_regions)()
+        t1 = (C.c_float * max_regions)()
+        n = _lib.check(self.lib.ka9q_stream_timer_timeline(self.h, max_regions, cls, t0, t1), "timer_timeline")
+        names = ("fft", "fm", "am", "linear", "bcast", "wait")
+        return [(names[cls[i]], t0[i], t1[i]) for i in range(n)]
 
     def nccl_init(self, id128: bytes, rank: int, nranks: int):
         buf = C.create_string_buffer(id128, 128)

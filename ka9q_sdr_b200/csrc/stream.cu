@@ -321,10 +321,20 @@ static int commit_impl(ka9q_stream* s) {
   K9_CUDA(cudaStreamCreateWithFlags(&s->s_fm, cudaStreamNonBlocking));
   K9_CUDA(cudaStreamCreateWithFlags(&s->s_am, cudaStreamNonBlocking));
   K9_CUDA(cudaStreamCreateWithFlags(&s->s_lin, cudaStreamNonBlocking));
-  K9_CUDA(cudaStreamCreateWithFlags(&s->s_fft, cudaStreamNonBlocking));
+  {
+    // The forward FFT (and the multi-GPU exchange behind it) of batch k+1 becomes runnable at about the same moment as the
+    // channel kernels of batch k. With equal priorities the channel kernels' long-lived CTAs (they loop over the blocks
+    // of the batch) take every slot first and the transform waits for them to drain; at a higher priority the transform
+    // goes first and the exchange then runs under the channel kernels. KA9Q_B200_FFT_PRIO=0 turns it off (A/B).
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    const char* ev = getenv("KA9Q_B200_FFT_PRIO");
+    const bool prio = ev ? atoi(ev) != 0 : false;  // (multi-GPU streams switch it on in ka9q_stream_mgpu_setup)
+    K9_CUDA(cudaStreamCreateWithPriority(&s->s_fft, cudaStreamNonBlocking, prio ? hi : lo));
+  }
   cudaEvent_t* evs[] = {&s->e_pushed, &s->e_fork, &s->e_am, &s->e_lin, &s->e_fm, &s->e_comp_done[0], &s->e_comp_done[1],
-                        &s->e_fetched[0], &s->e_fetched[1], &s->e_spec_ready[0], &s->e_spec_ready[1], &s->e_spec_free[0],
-                        &s->e_spec_free[1]};
+                        &s->e_fetched[0], &s->e_fetched[1], &s->e_spec_ready[0], &s->e_spec_ready[1], &s->e_spec_ready[2],
+                        &s->e_spec_free[0], &s->e_spec_free[1], &s->e_spec_free[2]};
   for (auto e : evs) K9_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   K9_CUDA(cudaEventCreate(&s->e_fft0));
   K9_CUDA(cudaEventCreate(&s->e_fft1));
@@ -334,7 +344,15 @@ static int commit_impl(ka9q_stream* s) {
   s->ring_cap = (long long)(M - 1) + 2LL * B * L;
   K9_CUDA(cudaMalloc(&s->d_ring, (size_t)s->ring_cap * s->bytes_per_samp));
   K9_CUDA(cudaMemset(s->d_ring, 0, (size_t)s->ring_cap * s->bytes_per_samp));  // zero history (filter.c:77)
-  K9_CUDA(cudaMalloc(&s->d_spec, sizeof(float2) * 2 * (size_t)B * N));  // double-buffered (see issue_fft)
+  {
+    // Spectrum buffers. Two: the FFT of batch k+1 under the channel kernels of batch k. Three (default): the FFT and, on
+    // multi-GPU runs, the exchange behind it may start a whole batch earlier, so that they are finished — however thinly
+    // they are scheduled beside the channel kernels' long-lived CTAs — before the channel kernels of their batch could
+    // start (measured at 2 GPUs: the exchange otherwise sits exposed between consecutive channel launches).
+    const char* ev = getenv("KA9Q_B200_SPEC_BUFFERS");
+    s->nspec = ev && atoi(ev) == 2 ? 2 : 3;
+  }
+  K9_CUDA(cudaMalloc(&s->d_spec, sizeof(float2) * s->nspec * (size_t)B * N));  // see issue_fft
   K9_CUDA(cudaMalloc(&s->d_tmp0, sizeof(float2) * (size_t)B * N));
   if (s->fwd.npass >= 3) K9_CUDA(cudaMalloc(&s->d_tmp1, sizeof(float2) * (size_t)B * N));
   K9_CUDA(cudaMalloc(&s->d_energy, sizeof(float) * B));
@@ -774,7 +792,7 @@ int issue_fft(ka9q_stream* s, long long first_block, int blk_first, int blk_coun
 // the spectrum buffer being written is complete (FFT and, on multi-GPU runs, the collective): hand it to the channels
 int publish_spectrum(ka9q_stream* s) {
   K9_CUDA(cudaEventRecord(s->e_spec_ready[s->spec_wr], s->s_fft));
-  s->spec_wr ^= 1;
+  s->spec_wr = (s->spec_wr + 1) % s->nspec;
   s->spec_published++;
   s->fft_pending = false;
   return 0;
@@ -880,7 +898,7 @@ int issue_channels(ka9q_stream* s, int nblocks) {
   if (s->n_pll) K9_CUDA(cudaStreamWaitEvent(s->s_comp, s->e_pll, 0));
   K9_CUDA(cudaEventRecord(s->e_chan1, s->s_comp));
   K9_CUDA(cudaEventRecord(s->e_spec_free[p], s->s_comp));
-  s->spec_rd ^= 1;
+  s->spec_rd = (s->spec_rd + 1) % s->nspec;
   s->phase_block += nblocks;
   s->comp_parity ^= 1;
   K9_CUDA(cudaEventRecord(s->e_comp_done[s->comp_parity], s->s_comp));
@@ -978,7 +996,9 @@ int ka9q_stream_sync(ka9q_stream* s) {
   K9_CUDA(cudaSetDevice(s->cfg.device));
   K9_CUDA(cudaStreamSynchronize(s->s_in));
   K9_CUDA(cudaStreamSynchronize(s->s_fft));
+  if (s->s_mgwait) K9_CUDA(cudaStreamSynchronize(s->s_mgwait));
   K9_CUDA(cudaStreamSynchronize(s->s_comp));
+  if (s->s_mgsig) K9_CUDA(cudaStreamSynchronize(s->s_mgsig));
   K9_CUDA(cudaStreamSynchronize(s->s_am));
   K9_CUDA(cudaStreamSynchronize(s->s_lin));
   if (s->s_n0) K9_CUDA(cudaStreamSynchronize(s->s_n0));
@@ -1009,7 +1029,7 @@ int ka9q_stream_last_timing(ka9q_stream* s, float* total_ms, float* fft_ms, floa
 int ka9q_stream_spectrum_ptr(ka9q_stream* s, void** dev_ptr, long long* bytes_per_block) {
   K9_CHECK(s && s->committed, "stream not committed");
   // the buffer compute_fft_only just wrote (not yet handed to the channel kernels), else the one the last launch read
-  if (dev_ptr) *dev_ptr = spec_buf(s, s->fft_pending ? s->spec_wr : (s->spec_rd ^ 1));
+  if (dev_ptr) *dev_ptr = spec_buf(s, s->fft_pending ? s->spec_wr : (s->spec_rd + s->nspec - 1) % s->nspec);
   if (bytes_per_block) *bytes_per_block = (long long)sizeof(float2) * s->N;
   return 0;
 }
@@ -1042,7 +1062,7 @@ int ka9q_stream_get_spectrum(ka9q_stream* s, int block, void* outN) {
   K9_CHECK(block >= 0 && block < s->cfg.max_blocks, "bad block");
   K9_CUDA(cudaSetDevice(s->cfg.device));
   if (ka9q_stream_sync(s)) return -1;
-  K9_CUDA(cudaMemcpy(outN, spec_buf(s, s->fft_pending ? s->spec_wr : (s->spec_rd ^ 1)) + (size_t)block * s->N, sizeof(float2) * s->N, cudaMemcpyDeviceToHost));
+  K9_CUDA(cudaMemcpy(outN, spec_buf(s, s->fft_pending ? s->spec_wr : (s->spec_rd + s->nspec - 1) % s->nspec) + (size_t)block * s->N, sizeof(float2) * s->N, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1081,14 +1101,16 @@ static void release_resources(ka9q_stream* s) {
     if (*p) cudaFreeHost(*p);
     *p = nullptr;
   }
-  cudaStream_t* sts[] = {&s->s_in, &s->s_comp, &s->s_out, &s->s_fm, &s->s_am, &s->s_lin, &s->s_fft, &s->s_n0, &s->s_pll};
+  cudaStream_t* sts[] = {&s->s_in, &s->s_comp, &s->s_out, &s->s_fm, &s->s_am, &s->s_lin, &s->s_fft, &s->s_n0, &s->s_pll,
+                         &s->s_mgwait, &s->s_mgsig};
   for (auto st : sts) {
     if (*st) cudaStreamDestroy(*st);
     *st = nullptr;
   }
   cudaEvent_t* evs[] = {&s->e_pushed, &s->e_fft0, &s->e_fft1, &s->e_chan1, &s->e_fork, &s->e_am, &s->e_lin, &s->e_fm,
                         &s->e_comp_done[0], &s->e_comp_done[1], &s->e_fetched[0], &s->e_fetched[1], &s->e_spec_ready[0],
-                        &s->e_spec_ready[1], &s->e_spec_free[0], &s->e_spec_free[1], &s->e_t0, &s->e_t1, &s->e_n0, &s->e_pll};
+                        &s->e_spec_ready[1], &s->e_spec_ready[2], &s->e_spec_free[0], &s->e_spec_free[1], &s->e_spec_free[2], &s->e_t0, &s->e_t1, &s->e_n0, &s->e_pll,
+                        &s->e_mg_ready, &s->e_mg_chan};
   for (auto e : evs) {
     if (*e) cudaEventDestroy(*e);
     *e = nullptr;
@@ -1131,7 +1153,15 @@ int ka9q_stream_timer_start(ka9q_stream* s) {
   s->ev_used.clear();
   s->ev_next = 0;
   s->timing = true;
+  s->timing_regions = true;
   K9_CUDA(cudaEventRecord(s->e_t0, s->s_comp));
+  return 0;
+}
+// the outer event pair only: nothing is recorded around the individual kernels (their event records cost a few
+// microseconds per step, which shows at 8-GPU step times); timer_stop then reports zeros for the classes
+int ka9q_stream_timer_start_plain(ka9q_stream* s) {
+  if (ka9q_stream_timer_start(s)) return -1;
+  s->timing_regions = false;
   return 0;
 }
 // ms_total: region time. class_ms[5] / class_launches[5]: summed device time and launch count of
@@ -1149,6 +1179,7 @@ int ka9q_stream_timer_stop(ka9q_stream* s, float* ms_total, float* class_ms, int
   int cnt[TC_COUNT] = {0, 0, 0, 0, 0};
   for (auto& u : s->ev_used) {
     float t = 0;
+    if (u.first >= TC_COUNT) continue;  // timeline-only regions (waits on peer flags)
     if (cudaEventElapsedTime(&t, u.second.first, u.second.second) == cudaSuccess) {
       acc[u.first] += t;
       cnt[u.first]++;
@@ -1159,6 +1190,26 @@ int ka9q_stream_timer_stop(ka9q_stream* s, float* ms_total, float* class_ms, int
     if (class_launches) class_launches[i] = cnt[i];
   }
   return 0;
+}
+
+// After timer_stop: the bracketed regions of the timed interval in issue order, as (class, start, end) in ms from
+// timer_start. Classes as in timer_stop, plus 5 = waiting for peer flags (multi-GPU). `start` is when the region's stream
+// reached it (its earlier work had finished), `end` when its last kernel had finished. Returns the number of regions.
+int ka9q_stream_timer_timeline(ka9q_stream* s, int max_regions, int* cls, float* start_ms, float* end_ms) {
+  K9_CHECK(s && s->committed && !s->timing && s->e_t0, "call after ka9q_stream_timer_stop");
+  K9_CUDA(cudaSetDevice(s->cfg.device));
+  int n = 0;
+  for (auto& u : s->ev_used) {
+    if (n >= max_regions) break;
+    float a = 0, b = 0;
+    if (cudaEventElapsedTime(&a, s->e_t0, u.second.first) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&b, s->e_t0, u.second.second) != cudaSuccess) continue;
+    cls[n] = u.first;
+    start_ms[n] = a;
+    end_ms[n] = b;
+    n++;
+  }
+  return n;
 }
 
 // ------------------------------------------------------------------ pinned host memory

@@ -15,9 +15,10 @@ using namespace k9;  // private header of two translation units
 constexpr int K9_MAX_RANKS = 16;
 
 // Channel-sharded multi-GPU state (mgpu.cu)
+constexpr int K9_MAX_SPEC = 3;           // spectrum buffers per stream (ka9q_stream::nspec of them in use)
 struct MgpuFlags {                       // lives in device memory of every rank, written by its peers over NVLink
-  int ready[2][K9_MAX_RANKS];            // [spectrum buffer][producer]: last batch whose sub-bands from that producer landed
-  int freed[2][K9_MAX_RANKS];            // [spectrum buffer][consumer]: last batch that consumer finished reading
+  int ready[K9_MAX_SPEC][K9_MAX_RANKS];  // [spectrum buffer][producer]: last batch whose sub-bands from that producer landed
+  int freed[K9_MAX_SPEC][K9_MAX_RANKS];  // [spectrum buffer][consumer]: last batch that consumer finished reading
   int error;                             // a wait timed out
   int pad[31];
 };
@@ -86,7 +87,11 @@ struct ka9q_stream {
   int comp_parity = 0;
   int last_nblocks = 0;
   cudaStream_t s_fft = nullptr;
-  cudaEvent_t e_spec_ready[2] = {nullptr, nullptr}, e_spec_free[2] = {nullptr, nullptr};
+  cudaStream_t s_mgwait = nullptr, s_mgsig = nullptr;  // multi-GPU: flag waits / flag signals, off the channel stream's critical path
+  cudaEvent_t e_mg_ready = nullptr, e_mg_chan = nullptr;
+  bool timing_regions = true;  // false: timer_start_plain, only the outer event pair is recorded
+  cudaEvent_t e_spec_ready[K9_MAX_SPEC] = {}, e_spec_free[K9_MAX_SPEC] = {};
+  int nspec = 3;  // spectrum buffers: the forward FFT (+ exchange) may run up to nspec - 1 batches ahead of the channel kernels
   int spec_wr = 0, spec_rd = 0, spec_published = 0;
   bool fft_pending = false;
   int fft_blocks_per_launch = 0;  // 0 = all blocks of the batch in one launch per pass (measured faster than per-block)
@@ -121,7 +126,7 @@ struct ka9q_stream {
   void* d_mg_jobs = nullptr;                         // copy-job list of the scatter kernel
   unsigned* d_mg_counter = nullptr;                  // CTAs of the scatter kernel that have finished
   int mg_njobs = 0, mg_jobs_nblocks = 0;
-  std::vector<CopyJob> mg_host_jobs[2];              // host copy of the job lists (copy-engine transport)
+  std::vector<CopyJob> mg_host_jobs[K9_MAX_SPEC];              // host copy of the job lists (copy-engine transport)
   bool mg_route_now = false;                         // set by mgpu_compute around its issue_fft
   bool mg_pull = false;                              // consumers load their arcs from the producers' buffers (default)
   bool mg_fused = false;                             // the forward FFT's last pass stores the arcs itself (no copy kernel)
@@ -156,7 +161,7 @@ extern const char* (*p_ncclGetErrorString)(int);
 int load_nccl();
 }
 
-enum TimeClass { TC_FFT = 0, TC_FM = 1, TC_AM = 2, TC_LIN = 3, TC_BCAST = 4, TC_COUNT = 5 };
+enum TimeClass { TC_FFT = 0, TC_FM = 1, TC_AM = 2, TC_LIN = 3, TC_BCAST = 4, TC_COUNT = 5, TC_WAIT = 5 };  // TC_WAIT: timeline only
 
 static inline cudaEvent_t timing_event(ka9q_stream* s) {
   if (s->ev_next == s->ev_pool.size()) {
@@ -171,7 +176,7 @@ struct TimedRegion {
   cudaStream_t st;
   cudaEvent_t e1 = nullptr;
   TimedRegion(ka9q_stream* s_, int cls, cudaStream_t st_) : s(s_), st(st_) {
-    if (!s->timing || s->ev_used.size() >= 4096) return;
+    if (!s->timing || !s->timing_regions || s->ev_used.size() >= 4096) return;
     cudaEvent_t e0 = timing_event(s);
     e1 = timing_event(s);
     if (!e0 || !e1) {
