@@ -81,6 +81,8 @@ def _worker(rank, world, port, mode, q, iq_path):
         os.environ["KA9Q_B200_MGPU_FUSED"] = "1"
     if mode == "p2p-pull":
         os.environ["KA9Q_B200_MGPU_PULL"] = "1"
+    if mode == "p2p-kernel":      # the exchange by this library's copy kernel instead of the (default) copy engines
+        os.environ["KA9Q_B200_MGPU_CE"] = "0"
     import ctypes as C
     import torch.distributed as dist
     from ka9q_sdr_b200 import channelizer as ch, mgpu, synth, workloads
@@ -96,7 +98,7 @@ def _worker(rank, world, port, mode, q, iq_path):
             c.add_channel(s.mode, s.bin, low=s.low, high=s.high)
         c.commit()
         pcm = np.empty((nb, c.pcm_stride), dtype=np.int16)
-        if mode in ("p2p", "nccl", "p2p-stream", "p2p-fused", "p2p-pull"):
+        if mode in ("p2p", "nccl", "p2p-stream", "p2p-fused", "p2p-pull", "p2p-kernel"):
             mgpu.setup_sharded(c, rank, world, ch.MGPU_NCCL if mode == "nccl" else ch.MGPU_P2P)
         else:  # "bcast": rank 0 transforms, ncclBroadcast of the whole spectrum
             ids = [ch.nccl_unique_id() if rank == 0 else None]
@@ -110,7 +112,7 @@ def _worker(rank, world, port, mode, q, iq_path):
                 part = np.ascontiguousarray(iq[2 * a:2 * (a + n)])
                 c.push_at(part.ctypes.data_as(C.c_void_p), a, n)
                 c.mgpu_compute(B, resident=False)
-            elif mode in ("p2p", "nccl", "p2p-fused", "p2p-pull"):
+            elif mode in ("p2p", "nccl", "p2p-fused", "p2p-pull", "p2p-kernel"):
                 c.push(blk.ctypes.data_as(C.c_void_p), B)
                 c.mgpu_compute(B, resident=True)
             else:
@@ -132,7 +134,7 @@ def _worker(rank, world, port, mode, q, iq_path):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("mode", ["p2p", "p2p-stream", "p2p-pull", "p2p-fused", "nccl", "bcast"])
+@pytest.mark.parametrize("mode", ["p2p", "p2p-stream", "p2p-kernel", "p2p-pull", "p2p-fused", "nccl", "bcast"])
 def test_sharded_two_gpus_equal_one_gpu(mode):
     import torch.multiprocessing as mp
     from ka9q_sdr_b200 import channelizer as ch, synth
