@@ -236,6 +236,15 @@ int ka9q_stream_mgpu_setup(ka9q_stream* s, int transport, int rank, int nranks, 
     }
     // flag waits and flag signals run on streams of their own: between two channel launches the channel stream then
     // only waits for an event instead of launching two one-warp kernels (about 10 us of an 8-GPU step)
+    {
+      const char* ex = getenv("KA9Q_B200_MGPU_XSTREAM");
+      if (!s->s_mgx && (!ex || atoi(ex) != 0)) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        K9_CUDA(cudaStreamCreateWithPriority(&s->s_mgx, cudaStreamNonBlocking, hi));
+        K9_CUDA(cudaEventCreateWithFlags(&s->e_mg_fft, cudaEventDisableTiming));
+      }
+    }
     if (!s->s_mgwait) K9_CUDA(cudaStreamCreateWithFlags(&s->s_mgwait, cudaStreamNonBlocking));
     if (!s->s_mgsig) K9_CUDA(cudaStreamCreateWithFlags(&s->s_mgsig, cudaStreamNonBlocking));
     if (!s->e_mg_ready) K9_CUDA(cudaEventCreateWithFlags(&s->e_mg_ready, cudaEventDisableTiming));
@@ -424,7 +433,7 @@ static int exchange_pull(ka9q_stream* s, int nblocks, int p, int seq) {
   return 0;
 }
 
-static int exchange_p2p(ka9q_stream* s, int nblocks, int p, int seq) {
+static int exchange_p2p(ka9q_stream* s, int nblocks, int p, int seq, cudaStream_t xs) {
   const int G = s->mg_nranks, me = s->mg_rank, cnt = nblocks / G;
   // copy-job list of this (parity, nblocks) shape, built once and cached on the device
   if (s->mg_jobs_nblocks != nblocks) {
@@ -457,8 +466,8 @@ static int exchange_p2p(ka9q_stream* s, int nblocks, int p, int seq) {
   }
   // the peers have finished reading their buffer p of two batches ago
   if (seq > s->nspec) {
-    TimedRegion tw(s, TC_WAIT, s->s_fft);
-    mgpu_wait_kernel<<<1, 32, 0, s->s_fft>>>(s->d_flags, 1, p, G, me, seq - s->nspec);
+    TimedRegion tw(s, TC_WAIT, xs);
+    mgpu_wait_kernel<<<1, 32, 0, xs>>>(s->d_flags, 1, p, G, me, seq - s->nspec);
   }
   static int ctas = 0, use_ce = -1;
   if (!ctas) {
@@ -475,12 +484,12 @@ static int exchange_p2p(ka9q_stream* s, int nblocks, int p, int seq) {
     // 2. KA9Q_B200_MGPU_CE=0 selects the copy kernel.
     const std::vector<CopyJob>& hj = s->mg_host_jobs[p];
     for (const CopyJob& j : hj)
-      K9_CUDA(cudaMemcpyAsync(j.dst, j.src, (size_t)j.n16 * 16, cudaMemcpyDeviceToDevice, s->s_fft));
-    mgpu_signal_ready_kernel<<<1, 32, 0, s->s_fft>>>(s->d_mg_peer_flag_ptrs, G, me, p, seq);
+      K9_CUDA(cudaMemcpyAsync(j.dst, j.src, (size_t)j.n16 * 16, cudaMemcpyDeviceToDevice, xs));
+    mgpu_signal_ready_kernel<<<1, 32, 0, xs>>>(s->d_mg_peer_flag_ptrs, G, me, p, seq);
     K9_CHECK(cudaGetLastError() == cudaSuccess, "signal kernel launch failed");
     return 0;
   }
-  mgpu_scatter_kernel<<<ctas, SCATTER_THREADS, 0, s->s_fft>>>((const CopyJob*)s->d_mg_jobs + (size_t)p * s->mg_njobs, s->mg_njobs,
+  mgpu_scatter_kernel<<<ctas, SCATTER_THREADS, 0, xs>>>((const CopyJob*)s->d_mg_jobs + (size_t)p * s->mg_njobs, s->mg_njobs,
                                                             s->d_mg_counter, s->d_mg_peer_flag_ptrs, G, me, p, seq);
   K9_CHECK(cudaGetLastError() == cudaSuccess, "scatter kernel launch failed");
   return 0;
@@ -522,6 +531,15 @@ int ka9q_stream_mgpu_compute(ka9q_stream* s, int nblocks, int resident) {
     TimedRegion tr(s, TC_BCAST, s->s_fft);
     mgpu_signal_ready_kernel<<<1, 32, 0, s->s_fft>>>(s->d_mg_peer_flag_ptrs, G, me, p, seq);
     K9_CHECK(cudaGetLastError() == cudaSuccess, "signal kernel launch failed");
+  } else if (G > 1 && s->mg_transport == KA9Q_MGPU_P2P && !pull && s->s_mgx) {
+    // The exchange runs on a stream of its own behind the transform: the FFT stream goes straight on to the next batch's
+    // transform instead of idling while the arcs travel (at 4 GPUs the channel kernels fill every SM, the transform only
+    // gets the SMs as they retire, and transform + exchange in one stream took longer than the channel kernels).
+    K9_CUDA(cudaEventRecord(s->e_mg_fft, s->s_fft));
+    K9_CUDA(cudaStreamWaitEvent(s->s_mgx, s->e_mg_fft, 0));
+    TimedRegion tr(s, TC_BCAST, s->s_mgx);
+    if (exchange_p2p(s, nblocks, p, seq, s->s_mgx)) return -1;
+    s->pub_stream = s->s_mgx;
   } else if (G > 1) {
     TimedRegion tr(s, TC_BCAST, s->s_fft);
     if (s->mg_transport == KA9Q_MGPU_NCCL) {
@@ -529,7 +547,7 @@ int ka9q_stream_mgpu_compute(ka9q_stream* s, int nblocks, int resident) {
     } else if (pull) {
       if (exchange_pull(s, nblocks, p, seq)) return -1;
     } else {
-      if (exchange_p2p(s, nblocks, p, seq)) return -1;
+      if (exchange_p2p(s, nblocks, p, seq, s->s_fft)) return -1;
     }
   }
   if (publish_spectrum(s)) return -1;

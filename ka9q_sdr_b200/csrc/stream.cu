@@ -791,7 +791,8 @@ int issue_fft(ka9q_stream* s, long long first_block, int blk_first, int blk_coun
 
 // the spectrum buffer being written is complete (FFT and, on multi-GPU runs, the collective): hand it to the channels
 int publish_spectrum(ka9q_stream* s) {
-  K9_CUDA(cudaEventRecord(s->e_spec_ready[s->spec_wr], s->s_fft));
+  K9_CUDA(cudaEventRecord(s->e_spec_ready[s->spec_wr], s->pub_stream ? s->pub_stream : s->s_fft));
+  s->pub_stream = nullptr;
   s->spec_wr = (s->spec_wr + 1) % s->nspec;
   s->spec_published++;
   s->fft_pending = false;
@@ -996,6 +997,7 @@ int ka9q_stream_sync(ka9q_stream* s) {
   K9_CUDA(cudaSetDevice(s->cfg.device));
   K9_CUDA(cudaStreamSynchronize(s->s_in));
   K9_CUDA(cudaStreamSynchronize(s->s_fft));
+  if (s->s_mgx) K9_CUDA(cudaStreamSynchronize(s->s_mgx));
   if (s->s_mgwait) K9_CUDA(cudaStreamSynchronize(s->s_mgwait));
   K9_CUDA(cudaStreamSynchronize(s->s_comp));
   if (s->s_mgsig) K9_CUDA(cudaStreamSynchronize(s->s_mgsig));
@@ -1102,7 +1104,7 @@ static void release_resources(ka9q_stream* s) {
     *p = nullptr;
   }
   cudaStream_t* sts[] = {&s->s_in, &s->s_comp, &s->s_out, &s->s_fm, &s->s_am, &s->s_lin, &s->s_fft, &s->s_n0, &s->s_pll,
-                         &s->s_mgwait, &s->s_mgsig};
+                         &s->s_mgwait, &s->s_mgsig, &s->s_mgx};
   for (auto st : sts) {
     if (*st) cudaStreamDestroy(*st);
     *st = nullptr;
@@ -1110,7 +1112,7 @@ static void release_resources(ka9q_stream* s) {
   cudaEvent_t* evs[] = {&s->e_pushed, &s->e_fft0, &s->e_fft1, &s->e_chan1, &s->e_fork, &s->e_am, &s->e_lin, &s->e_fm,
                         &s->e_comp_done[0], &s->e_comp_done[1], &s->e_fetched[0], &s->e_fetched[1], &s->e_spec_ready[0],
                         &s->e_spec_ready[1], &s->e_spec_ready[2], &s->e_spec_free[0], &s->e_spec_free[1], &s->e_spec_free[2], &s->e_t0, &s->e_t1, &s->e_n0, &s->e_pll,
-                        &s->e_mg_ready, &s->e_mg_chan};
+                        &s->e_mg_ready, &s->e_mg_chan, &s->e_mg_fft};
   for (auto e : evs) {
     if (*e) cudaEventDestroy(*e);
     *e = nullptr;

@@ -87,6 +87,8 @@ struct ka9q_stream {
   int comp_parity = 0;
   int last_nblocks = 0;
   cudaStream_t s_fft = nullptr;
+  cudaStream_t s_mgx = nullptr, pub_stream = nullptr;  // multi-GPU: exchange stream; stream the next publish_spectrum records on
+  cudaEvent_t e_mg_fft = nullptr;
   cudaStream_t s_mgwait = nullptr, s_mgsig = nullptr;  // multi-GPU: flag waits / flag signals, off the channel stream's critical path
   cudaEvent_t e_mg_ready = nullptr, e_mg_chan = nullptr;
   bool timing_regions = true;  // false: timer_start_plain, only the outer event pair is recorded
