@@ -617,7 +617,8 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
 #endif
 #if FM_TMA == 2
   // prefetch pipeline: the window of the next channel-job is copied while the current one is transformed
-  if (t == 0 && a.nblocks > 0 && use_tma) tma_issue_window(sh.land, a.spec, (int)sh.P[0].bin, &sh.tma_bar);
+  if (t == 0 && e0 < a.nblocks && use_tma)
+    tma_issue_window(sh.land, a.spec + (long long)e0 * a.spec_stride, (int)sh.P[0].bin, &sh.tma_bar);
 #endif
   // Audio-history rings of the pair (2048 floats each). An absent channel B reads the spare all-zero ring that follows
   // the last channel's; nothing is ever written to it.
@@ -657,8 +658,8 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
           if (t == 0) {
             if (h == 0 && wk.y >= 0)
               tma_issue_window(sh.land, X, (int)sh.P[1].bin, &sh.tma_bar);
-            else if (b + 1 < a.nblocks)
-              tma_issue_window(sh.land, X + a.spec_stride, (int)sh.P[0].bin, &sh.tma_bar);
+            else if (b + split < a.nblocks)  // this CTA's next block
+              tma_issue_window(sh.land, X + (long long)split * a.spec_stride, (int)sh.P[0].bin, &sh.tma_bar);
           }
         } else
 #endif
