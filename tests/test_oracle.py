@@ -217,3 +217,43 @@ def test_cpu_channelizer_restatement_matches_the_per_channel_port():
         d = np.abs(got[i].astype(np.int32) - want.astype(np.int32))
         assert d.max() <= 1, (k, d.max())
         assert np.abs(want).max() > 1000
+
+
+@pytest.mark.parametrize("eps", [0.37, -0.5, 0.0])
+def test_off_grid_lo_identity_against_the_reference(ref, eps):
+    """DESIGN.md section 1.2, pinned on the CPU: the reference mixing with an arbitrary-double second LO ahead of its own
+    FFT (radio.c:217,299) equals — to its own fp32 rounding — the shared-FFT form: bin rotation by the nearest grid bin k,
+    the channel's impulse response times exp(+j 2 pi eps m / 2048), the kept samples times exp(-j 2 pi eps n' / 2048).
+    float64 numpy on one side, the verbatim reference (oracle/_ref) on the other."""
+    fs = 192000
+    D, L, M, N = synth.geometry(fs)
+    nb, k = 6, 1024
+    n = nb * L
+    rng = np.random.default_rng(5)
+    fc = (k + eps) * fs / N
+    x = (synth.fm_carrier(n, fs, fc, 1000.0, 3000.0, 0.2) + synth.fm_carrier(n, fs, fc + 9000, 700.0, 2500.0, 0.2)
+         + synth.awgn(rng, n, 0.01))
+    iq = synth._quantize(x)
+    want = ref.chain_run("FM", fs, L, M, D, iq, carrier_hz=fc, want_filt=True).filt[:nb]
+    xs = (iq[0::2].astype(np.float64) + 1j * iq[1::2]) / 32767.0
+    m = modes.get_mode("FM")
+    nd, md, olen = N // D, (M - 1) // D + 1, L // D
+    f = np.fft.fftfreq(nd)
+    H = ((f >= m.low / (fs / D)) & (f <= m.high / (fs / D))).astype(np.complex128) / N      # filter.c:518-535
+    h = np.fft.ifft(H) * nd                                                                 # unnormalised backward
+    w = np.asarray(port.make_kaiser(md, 3.0), dtype=np.float64)
+    hh = np.zeros(nd, complex)
+    idx = np.arange(md)
+    hh[:md] = h[(idx - md // 2) % nd] * w / nd                                              # filter.c:386-392
+    hh[:md] *= np.exp(2j * np.pi * eps * idx / nd)                                          # the phase ramp
+    R = np.fft.fft(hh)
+    buf = np.concatenate([np.zeros(M - 1, complex), xs])
+    s = np.arange(nd)
+    s = np.where(s <= nd // 2, s, s - nd)
+    for b in range(nb):
+        X = np.fft.fft(buf[b * L:b * L + N])
+        y = np.fft.ifft(X[(k + s) % N] * R) * nd
+        y = y * np.exp(2j * np.pi * ((-k * (b * L - (M - 1))) % N) / N)                     # SURVEY Appendix C
+        yk = y[nd - olen:] * np.exp(-2j * np.pi * eps * (b * olen + np.arange(olen)) / nd)  # rotation at the output rate
+        err = np.linalg.norm(yk - want[b]) / np.linalg.norm(want[b])
+        assert err < 5e-7, (eps, b, err)
