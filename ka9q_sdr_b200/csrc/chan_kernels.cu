@@ -540,8 +540,8 @@ __device__ __noinline__ void fm_flat_output(const float* audA, const float* audB
 // A cluster of `fm_split` CTAs shares one pair: CTA e takes blocks b = e (mod split). The transforms of different blocks
 // are independent; what chains the blocks of a channel is small: the discriminator / squelch state (ChanState) and the
 // audio ring. So block b's CTA runs its first predetection transform at once, then waits until block b-1's CTA has (1)
-// finished both discriminators and (2) loaded its own 2048-sample audio window out of the ring (block b's audio
-// overwrites the oldest part of that window). State travels through a.state[], the order through one sequence number
+// finished both discriminators and (2) read its own 2048-sample audio window out of the ring and used it (block b's
+// audio overwrites the oldest part of that window). State travels through a.state[], the order through one sequence number
 // per pair (absolute block count, release / acquire at GPU scope). The cluster guarantees that the CTAs are co-resident.
 // want: blocks of this pair discriminated since stream start, as the block about to be discriminated needs it
 __device__ __noinline__ void fm_split_wait(const long long* f, const ChanState* state, long long want, FmShared& sh, int2 wk) {
@@ -682,7 +682,6 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
             // (block-split form: the older part of the window was written by another CTA, so no L1)
             v[8 * e + r] = SPLIT ? make_float2(__ldcg(histA + ri), -__ldcg(histB + ri)) : make_float2(histA[ri], -histB[ri]);
           }
-        if (SPLIT) fm_split_signal(a.fm_seq + pairi, a.state, m + 1, sh, wk);  // the next block's discriminators may overwrite the ring now
       }
       // the buffer's previous readers are a barrier behind us except after job 2 (its last stage just read it)
       fft2048<+1>(v, sh.buf, a.tw2048, sh.tw2, !FM_FEWER_BARRIERS || job == 3 || (FM_TMA == 1 && job < 2));
@@ -700,6 +699,10 @@ __global__ void __launch_bounds__(FFT2048_THREADS, FM_CTAS_PER_SM) fm_kernel(con
           sh.ephase[h] = ep;
         }
       } else if (job == 2) {
+        // Block-split form: the next block's discriminators may overwrite the ring from here on. Signalled only now, after
+        // the forward transform has consumed the window: a barrier does not wait for loads still in flight, the
+        // transform's first exchange through shared memory does (every value of the window has been used).
+        if (SPLIT) fm_split_signal(a.fm_seq + pairi, a.state, m + 1, sh, wk);
         if (a.pl_spec) {  // PL-tone analyser enabled: the low bins of Z = FFT(audA + j audB) for pl_kernel (Z = conj(v))
           float2* o = a.pl_spec + ((long long)b * a.pl_npairs + pairi) * 65;
           if (t <= 32) o[t] = make_float2(v[0].x, -v[0].y);
