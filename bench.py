@@ -709,7 +709,19 @@ def run_ours(args, plan):
         line["weak"] = weak
     if sharded:
         arc_lo, arc_len = arc
-        line["exchange"] = {"transport": args.transport, "arc_bins_this_rank": arc_len,
+        if args.transport != "p2p":
+            form = "grouped ncclSend / ncclRecv of the arcs"
+        elif os.environ.get("KA9Q_B200_MGPU_FUSED", "0") not in ("", "0"):
+            form = "arcs stored into the peers' HBM by the forward FFT's last pass (fused)"
+        elif os.environ.get("KA9Q_B200_MGPU_PULL", "0") not in ("", "0"):
+            form = "consumers load their arcs out of the producers' HBM (pull kernel)"
+        elif os.environ.get("KA9Q_B200_MGPU_CE", "1") in ("", "0"):
+            form = "arcs stored into the peers' HBM by this library's copy kernel; flags at system scope"
+        else:
+            form = "peer-to-peer copy-engine transfers of the arcs into the peers' HBM + this library's flag kernels (default)"
+        line["exchange"] = {"transport": args.transport, "form": form, "arc_bins_this_rank": arc_len,
+                            "pipeline": "FFT and exchange of later batches run under the channel kernels of the current one "
+                                        "(3 spectrum buffers, high-priority FFT / exchange streams; DESIGN.md section 7)",
                             "nvlink_bytes_in_per_step_this_rank": int(arc_len * 8 * B * (world - 1) / world),
                             "broadcast_would_move_bytes_per_step": int(plan.N * 8 * B * (world - 1) / world)}
     print(json.dumps(line))
