@@ -667,7 +667,20 @@ def run_ours(args, plan):
             cpu_chan = {"error": str(e)}
 
     launches_per_step = launches_pc + ((4 if args.transport == "p2p" else 1) if sharded else (1 if multi and not replicate else 0))
-    work_mb = (K * 2048 * 8 + K * 2048 * 4 + B * plan.N * 8 * 2 + B * pcm_stride * 2) / 1e6
+    if sharded and multi:
+        # per GPU: audio rings, the arc of the B spectra its channels read, its own blocks' transform (input, two scratch
+        # buffers, output), its PCM rows
+        bown = B // world
+        work_mb = (K * 2048 * 4 + arc[1] * 8 * B + bown * (plan.L * 4 + plan.N * 8 * 3) + B * pcm_stride * 2) / 1e6
+    else:
+        work_mb = (K * 2048 * 8 + K * 2048 * 4 + B * plan.N * 8 * 2 + B * pcm_stride * 2) / 1e6
+    if work_mb > 126:
+        l2_note = f"per-step working set {work_mb:.0f} MB > 126 MB L2 (responses+state+spectra+PCM); no flush needed"
+    else:
+        l2_note = (f"per-GPU working set of a step {work_mb:.0f} MB, of the order of the 126 MB L2 and rewritten every step "
+                   "(the peers store fresh spectrum arcs over NVLink, the PCM rows are overwritten); no flush: the channel "
+                   "kernels are bound by the L1 data pipe with DRAM at 7 % (DESIGN.md section 3), so L2 residency does not "
+                   "move this number")
     line = {
         "metric": METRIC, "value": ms_blocks_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -680,15 +693,16 @@ def run_ours(args, plan):
                        "sharded": f"{K_total} channels sharded frequency-contiguously over {world} GPUs (strong scaling); "
                                   f"forward FFT sharded by block ({B // world} of {B} blocks per rank and step); every "
                                   "producer sends each peer only the arc of the spectrum its channels read: "
-                                  + ("peer-memory stores over NVLink from a copy kernel of this library + device-memory "
-                                     "sequence flags (no collective library on the data path)" if args.transport == "p2p"
+                                  + ("peer-memory stores over NVLink (copy engines by default, this library's copy kernel with "
+                                     "KA9Q_B200_MGPU_CE=0) + device-memory sequence flags raised by this library's kernels "
+                                     "(no collective library on the data path)" if args.transport == "p2p"
                                      else "grouped ncclSend/ncclRecv"),
                        "replicate": f"channels x{world} (weak); every rank ingests the int16 stream and runs its own "
                                     "forward FFT, no data-path collective",
                        "allgather": f"channels x{world} (weak); forward FFT sharded by block + NCCL all-gather of spectra",
                        "broadcast": f"channels x{world} (weak); NCCL spectrum broadcast from rank 0"}[args.mgpu],
                    **({"cpus_bound_per_rank": numa} if numa else {}),
-                   "l2": f"per-step working set {work_mb:.0f} MB > 126 MB L2 (responses+state+spectra+PCM); no flush needed"},
+                   "l2": l2_note},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
