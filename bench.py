@@ -355,11 +355,21 @@ def run_ours(args, plan):
     if multi:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    B = args.blocks
+    B = args.blocks if args.blocks else 4
     sharded = multi and args.mgpu == "sharded"
     if multi and args.mgpu in ("allgather", "sharded"):
         B = max(B, world)
         B += (-B) % world          # the block-sharded forward FFT needs blocks_per_step % n_gpus == 0
+    if sharded and not args.blocks:
+        # Strong scaling shrinks the per-GPU share of a step; keep it larger than the 126 MB L2 (timing rule: no step may
+        # run out of a warm L2) by batching more blocks per step: 4 / 4 / 8 / 16 blocks at 1 / 2 / 4 / 8 GPUs on cfg5.
+        def per_gpu_bytes(nb):
+            kr = len(plan.channels) / world
+            olen = plan.L // plan.D
+            return (kr * 2048 * 4 + (plan.N / world + 2048) * 8 * nb + (nb // world) * (plan.L * 4 + plan.N * 8 * 3)
+                    + nb * kr * olen * 2)
+        while per_gpu_bytes(B) < 1.05 * 126e6 and B < 8 * world:
+            B += world
     from ka9q_sdr_b200 import workloads
     my_channels = workloads.shard_contiguous(plan, rank, world) if sharded else plan.channels
     c = ch.Channelizer(plan.samprate, plan.L, plan.M, plan.D, device=local, max_blocks=B)
@@ -579,7 +589,7 @@ def run_ours(args, plan):
     if multi and args.weak:
         c.close()
         wplan = make_plan(args.config, args.channels) if args.config != "cfg5" else workloads.cfg5(args.channels or 8192, 16 * rank)
-        Bw = args.blocks
+        Bw = args.blocks if args.blocks else 4
         cw = ch.Channelizer(wplan.samprate, wplan.L, wplan.M, wplan.D, device=local, max_blocks=Bw)
         for spec in wplan.channels:
             cw.add_channel(spec.mode, spec.bin, low=spec.low, high=spec.high)
@@ -752,7 +762,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg5")
     ap.add_argument("--channels", type=int, default=None)
-    ap.add_argument("--blocks", type=int, default=4, help="20 ms blocks per step")
+    ap.add_argument("--blocks", type=int, default=None,
+                    help="20 ms blocks per step (default 4; sharded multi-GPU runs grow it until a rank's share of a step "
+                         "exceeds L2)")
     ap.add_argument("--e2e-steps", type=int, default=100,
                     help="timed steps of the end-to-end leg (the last batch's copy-out drains inside the timed region)")
     ap.add_argument("--ref-blocks", type=int, default=0)
